@@ -1,0 +1,123 @@
+// cspm_internal.h — host-side handle types shared by the translation units of
+// libcspm_b200.so.  Not installed; the public surface is include/cspm_c.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cspm_c.h"
+#include "cspm_device.cuh"
+
+namespace cspm {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+#define CSPM_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      throw ::cspm::Error(e__ == cudaErrorMemoryAllocation ? CSPM_ENOMEM : CSPM_ENODEV,          \
+                          std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+  } while (0)
+
+#define CSPM_REQUIRE(cond, msg)                                    \
+  do {                                                             \
+    if (!(cond)) throw ::cspm::Error(CSPM_EINVAL, std::string(msg)); \
+  } while (0)
+
+// Run body, translate exceptions into the C error convention.
+template <typename F>
+int guard(F&& f) {
+  try {
+    f();
+    return CSPM_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return CSPM_ENODEV;
+  }
+}
+template <typename T, typename F>
+T* guard_ptr(F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return nullptr;
+  }
+}
+
+// Selects the device for the current thread and checks it exists.  This is
+// where a box without a GPU fails loudly (no CPU fallback anywhere).
+void use_device(int device);
+
+struct DeviceArena {
+  std::vector<void*> ptrs;
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    CSPM_CUDA(cudaMalloc(&p, n * sizeof(T) + 256));  // slack: vector loads may touch the tail
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+}  // namespace cspm
+
+struct cspm_cc {
+  int kind;  // cspm::CcKind
+  std::string name;
+};
+
+struct cspm_pc {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cspm::PcDev dev{};
+  int wnd_size = 35;
+  int scale_num = 1;  // 1 for PreSSPC
+  std::vector<double> scale_wgt;
+  double max_cost[2][cspm::kMaxScales] = {};
+  int dims[cspm::kMaxScales][3] = {};
+  uint8_t* d_bgr[2][cspm::kMaxScales] = {};  // dense 8-bit BGR pyramid (device)
+  cspm::DeviceArena arena;
+  mutable cspm_stats_t stats{};
+  // Sum over pixels of the in-image window size, per scale (for tap counting).
+  uint64_t taps_per_image_eval = 0;
+};
+
+struct cspm_pm {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int w = 0, h = 0, max_dis = 0, dis_scale = 1, schedule = 0, n_ref = 0;
+  uint64_t seed = 0;
+  double* st[2] = {nullptr, nullptr};  // 7 planes of w*h: nx ny nz a b c cost
+  uint8_t* dis[2] = {nullptr, nullptr};
+  uint8_t* d_bgr[2] = {nullptr, nullptr};  // dense BGR copies (post-processing weights)
+  // view-propagation scratch
+  double* cand_cost = nullptr;
+  int* cand_tx = nullptr;
+  unsigned long long* tmin = nullptr;
+  unsigned int* win = nullptr;
+  unsigned long long* tap_counter = nullptr;
+  // post-processing scratch
+  int* valid[2] = {nullptr, nullptr};
+  uint8_t* dis_tmp = nullptr;
+  cspm::DeviceArena arena;
+  cspm_stats_t stats{};
+  float stage_ms[6] = {};
+};

@@ -1,0 +1,662 @@
+// cspm_pm.cu — CSPatchMatch side of libcspm_b200.so: the PatchMatch driver
+// loop (cs_patchmatch.cc:51-109) as CUDA kernels.
+//
+//   k_init            InitRandomPlane     (:115-148)   thread per pixel
+//   k_spatial_diag    SpatialPropagation  (:163-216)   anti-diagonal wavefront,
+//                                                      one CTA per pixel
+//   k_view_*          ViewPropagation     (:229-277)   scatter + ordered resolve
+//   k_refine          PlaneRefinement     (:292-345)   thread per pixel, all
+//                                                      n_ref halvings fused
+//   k_plane2disp      PlaneToDisp         (:590-602)
+//   k_pp_*            PostProcessing      (:347-588)
+//
+// Every stage reproduces the reference's serial semantics exactly (see
+// DESIGN.md "Schedules"), so planes, costs and disparities are bit-identical
+// to the reference code run with the same RNG streams.
+#include <algorithm>
+#include <cstring>
+
+#include "cspm_internal.h"
+
+namespace cspm {
+
+struct PmDev {
+  int w, h, max_dis, n_ref, dis_scale;
+  uint64_t seed;
+  double* st[2];  // 7 planes of w*h: nx ny nz a b c cost
+};
+
+__device__ __forceinline__ PlaneD load_plane(const double* st, size_t n, size_t i) {
+  PlaneD p;
+  p.nx = st[i]; p.ny = st[n + i]; p.nz = st[2 * n + i];
+  p.a = st[3 * n + i]; p.b = st[4 * n + i]; p.c = st[5 * n + i];
+  return p;
+}
+__device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, const PlaneD& p, double cost) {
+  st[i] = p.nx; st[n + i] = p.ny; st[2 * n + i] = p.nz;
+  st[3 * n + i] = p.a; st[4 * n + i] = p.b; st[5 * n + i] = p.c;
+  st[6 * n + i] = cost;
+}
+
+// ------------------------------------------------------------------- init
+__global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
+  __shared__ double s_lut_w[kLutW];
+  __shared__ double s_lut_c[kLutC];
+  stage_luts(pc, s_lut_w, s_lut_c);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int v = blockIdx.z;
+  if (x >= pm.w || y >= pm.h) return;
+  const uint64_t stream = stream_init(pm.h, v, y);
+  // rng.uniform(kDoubleEps, max_dis)  (:134-135)
+  const double z = rng_uniform(pm.seed, stream, 2u * x, 0, kDoubleEps, (double)pm.max_dis);
+  double rn[3];
+  rng_normal3(pm.seed, stream, 2u * x + 1, 0.0, 1.0, rn);  // (:138)
+  const double denom = fmax(norm_l2(rn[0], rn[1], rn[2]), kDoubleEps);
+  const double inv = ddiv(1.0, denom);  // Vec / double multiplies by the reciprocal
+  PlaneD p;
+  p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
+  update_param(p, (double)x, (double)y, z);
+  const double cost = plane_cost(pc, v, x, y, p, s_lut_w, s_lut_c);
+  store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
+}
+
+// ----------------------------------------------------------------- refine
+__global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
+  __shared__ double s_lut_w[kLutW];
+  __shared__ double s_lut_c[kLutC];
+  stage_luts(pc, s_lut_w, s_lut_c);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int v = blockIdx.z;
+  if (x >= pm.w || y >= pm.h) return;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  PlaneD cur = load_plane(pm.st[v], n, i);
+  double cur_cost = pm.st[v][6 * n + i];
+  double z_iter = ddiv((double)pm.max_dis, 2.0), n_iter = 1.0;  // kMaxNorm_
+  for (int step = 0; step < pm.n_ref; ++step) {
+    const uint64_t stream = stream_refine(pm.h, pm.n_ref, iter, step, v, y);
+    const double dz = rng_uniform(pm.seed, stream, 2u * x, 0, -z_iter, z_iter);
+    const double z = dadd(plane_disp(cur, x, y), dz);
+    PlaneD q;
+    q.nx = dadd(cur.nx, rng_uniform(pm.seed, stream, 2u * x + 1, 0, -n_iter, n_iter));
+    q.ny = dadd(cur.ny, rng_uniform(pm.seed, stream, 2u * x + 1, 1, -n_iter, n_iter));
+    q.nz = dadd(cur.nz, rng_uniform(pm.seed, stream, 2u * x + 1, 2, -n_iter, n_iter));
+    const double denom = fmax(norm_l2(q.nx, q.ny, q.nz), kDoubleEps);
+    const double inv = ddiv(1.0, denom);
+    q.nx = dmul(q.nx, inv); q.ny = dmul(q.ny, inv); q.nz = dmul(q.nz, inv);
+    update_param(q, (double)x, (double)y, z);
+    const double cost = plane_cost(pc, v, x, y, q, s_lut_w, s_lut_c);
+    if (cost < cur_cost) {
+      cur = q;
+      cur_cost = cost;
+    }
+    z_iter = ddiv(z_iter, 2.0);
+    n_iter = ddiv(n_iter, 2.0);
+  }
+  store_plane(pm.st[v], n, i, cur, cur_cost);
+}
+
+// ---------------------------------------------------------------- spatial
+// One anti-diagonal of the serial raster scan.  Pixel (u,t) in scan
+// coordinates (u+t == diag) depends only on (u-1,t) and (u,t-1), both final
+// on the previous diagonal, so all pixels of a diagonal run concurrently and
+// the result equals the sequential Gauss-Seidel sweep.  One CTA per pixel:
+// phase 1 computes every window tap's addend in parallel, phase 2 adds them
+// in the reference's row-major order (one thread per candidate), so the sum
+// is rounded exactly like the scalar loop.
+__global__ void __launch_bounds__(128) k_spatial_diag(PcDev pc, PmDev pm, int diag, int u_lo, int rev) {
+  extern __shared__ double s_dyn[];
+  double* s_lut_w = s_dyn;
+  double* s_lut_c = s_lut_w + kLutW;
+  double* s_terms = s_lut_c + kLutC;  // [2][wnd*wnd]
+  __shared__ double s_cost[2];
+  stage_luts(pc, s_lut_w, s_lut_c);
+
+  const int v = blockIdx.y;
+  const int u = u_lo + blockIdx.x, t = diag - u;
+  const int x = rev ? pm.w - 1 - u : u, y = rev ? pm.h - 1 - t : t;
+  const int inc = rev ? -1 : 1;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  const bool has[2] = {u >= 1, t >= 1};
+  PlaneD cand[2];
+  if (has[0]) cand[0] = load_plane(pm.st[v], n, i - inc);                      // (x - x_inc, y)
+  if (has[1]) cand[1] = load_plane(pm.st[v], n, i - (ptrdiff_t)inc * pm.w);    // (x, y - y_inc)
+
+  const int wnd = 2 * pc.half_wnd + 1, wtaps = wnd * wnd;
+  double cost[2] = {0.0, 0.0};
+  double cur_disp[2];
+  for (int c = 0; c < 2; ++c) cur_disp[c] = has[c] ? plane_disp(cand[c], x, y) : 0.0;
+  int cx = x, cy = y;
+  for (int s = 0; s < pc.scale_num; ++s) {
+    const ScaleDev& sc = pc.sc[s];
+    const TapCtx tc = make_tap_ctx(pc, s, v, s_lut_w, s_lut_c);
+    PlaneD q[2];
+    for (int c = 0; c < 2; ++c) {
+      q[c] = cand[c];
+      if (pc.cross_scale && has[c]) update_param(q[c], (double)cx, (double)cy, cur_disp[c]);
+    }
+    const uint32_t Ip = tc.col_v[cy * sc.pitch + sc.pad + cx];
+    for (int k = threadIdx.x; k < 2 * wtaps; k += blockDim.x) {
+      const int c = k / wtaps, tap = k - c * wtaps;
+      if (!has[c]) continue;
+      const int qy = cy + tap / wnd - pc.half_wnd, qx = cx + tap % wnd - pc.half_wnd;
+      double term = 0.0;  // +0.0 is the additive identity for these non-negative sums
+      if (qy >= 0 && qy < sc.h && qx >= 0 && qx < sc.w) {
+        const double q_disp_y = dadd(dmul(q[c].b, (double)qy), q[c].c);
+        term = tap_term(tc, qy * sc.pitch + sc.pad, qx, Ip, q[c].a, q_disp_y);
+      }
+      s_terms[k] = term;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < 64) {
+      const int c = threadIdx.x >> 5;
+      if (has[c]) {
+        double sum = 0.0;
+        const double* tp = s_terms + c * wtaps;
+        for (int k = 0; k < wtaps; ++k) sum = dadd(sum, tp[k]);
+        s_cost[c] = sum;
+      }
+    }
+    __syncthreads();
+    for (int c = 0; c < 2; ++c) {
+      if (!has[c]) continue;
+      if (pc.cross_scale) cost[c] = dadd(cost[c], dmul(s_cost[c], pc.scale_wgt[s]));
+      else cost[c] = s_cost[c];
+      cur_disp[c] = ddiv(cur_disp[c], 2.0);
+    }
+    cx /= 2;
+    cy /= 2;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double min_cost = pm.st[v][6 * n + i];
+    int best = -1;
+    if (has[0] && cost[0] < min_cost) { min_cost = cost[0]; best = 0; }   // x-axis neighbour first (:198-204)
+    if (has[1] && cost[1] < min_cost) { min_cost = cost[1]; best = 1; }   // then y-axis neighbour (:206-212)
+    if (best >= 0) store_plane(pm.st[v], n, i, cand[best], min_cost);
+  }
+}
+
+// ------------------------------------------------------------------- view
+// ViewPropagation for reference view v: every pixel (x,y) of the OTHER view
+// proposes its plane to (cor_x, y).  Sequentially the target keeps the lowest
+// cost and, among equal costs, the proposal met first in scan order (strict
+// `<`, :270); the original plane wins ties.  Parallel form: evaluate all
+// proposals, atomicMin the cost bits per target, then atomicMin the scan
+// position among the proposals that hit the minimum, then the winner writes.
+__global__ void k_view_begin(PmDev pm, int v, unsigned long long* tmin, unsigned int* win) {
+  const size_t n = (size_t)pm.w * pm.h;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tmin[i] = (unsigned long long)__double_as_longlong(pm.st[v][6 * n + i]);
+  win[i] = 0xFFFFFFFFu;
+}
+__device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, int y, PlaneD* q, int* cor_x) {
+  const size_t n = (size_t)pm.w * pm.h;
+  const PlaneD o = load_plane(pm.st[1 - v], n, (size_t)y * pm.w + x);
+  double disp = plane_disp(o, x, y);
+  if (disp < 0.0) disp = 0.0;
+  if (disp >= pm.max_dis) disp = dsub((double)pm.max_dis, 1.0);
+  const int r = round2int(disp);
+  *cor_x = handle_border(v == 0 ? x + r : x - r, pm.w);
+  *q = o;
+  update_param(*q, (double)*cor_x, (double)y, disp);
+}
+__global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
+                                                   unsigned long long* tmin, unsigned long long* tap_counter) {
+  __shared__ double s_lut_w[kLutW];
+  __shared__ double s_lut_c[kLutC];
+  stage_luts(pc, s_lut_w, s_lut_c);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  unsigned long long taps = 0;
+  if (x < pm.w && y < pm.h) {
+    PlaneD q;
+    int cor_x;
+    view_candidate(pm, v, x, y, &q, &cor_x);
+    const double cost = plane_cost(pc, v, cor_x, y, q, s_lut_w, s_lut_c);
+    const size_t i = (size_t)y * pm.w + x;
+    cand_cost[i] = cost;
+    cand_tx[i] = cor_x;
+    atomicMin(&tmin[(size_t)y * pm.w + cor_x], (unsigned long long)__double_as_longlong(cost));
+    int cx = cor_x, cy = y;
+    for (int s = 0; s < pc.scale_num; ++s) {
+      const ScaleDev& sc = pc.sc[s];
+      taps += (unsigned long long)(min(cx + pc.half_wnd, sc.w - 1) - max(cx - pc.half_wnd, 0) + 1) *
+              (min(cy + pc.half_wnd, sc.h - 1) - max(cy - pc.half_wnd, 0) + 1);
+      cx /= 2; cy /= 2;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) taps += __shfl_xor_sync(0xffffffffu, taps, o);
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && taps) atomicAdd(tap_counter, taps);
+}
+__global__ void k_view_resolve(PmDev pm, int v, int rev, const double* cand_cost, const int* cand_tx,
+                               const unsigned long long* tmin, unsigned int* win) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= pm.w) return;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  const size_t t = (size_t)y * pm.w + cand_tx[i];
+  const double cost = cand_cost[i];
+  if ((unsigned long long)__double_as_longlong(cost) == tmin[t] && cost < pm.st[v][6 * n + t])
+    atomicMin(&win[t], (unsigned int)(rev ? pm.w - 1 - x : x));
+}
+__global__ void k_view_commit(PmDev pm, int v, int rev, const double* cand_cost, const int* cand_tx,
+                              const unsigned int* win) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= pm.w) return;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  const size_t t = (size_t)y * pm.w + cand_tx[i];
+  if (win[t] != (unsigned int)(rev ? pm.w - 1 - x : x)) return;
+  PlaneD q;
+  int cor_x;
+  view_candidate(pm, v, x, y, &q, &cor_x);
+  store_plane(pm.st[v], n, t, q, cand_cost[i]);
+}
+
+// -------------------------------------------------------------- plane2disp
+__global__ void k_plane2disp(PmDev pm, uint8_t* dis0, uint8_t* dis1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= pm.w) return;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  const double* st = pm.st[v];
+  // param().dot(Vec3d(x, y, 1.0)): s = 0; s += a*x; s += b*y; s += c*1.0
+  double d = 0.0;
+  d = dadd(d, dmul(st[3 * n + i], (double)x));
+  d = dadd(d, dmul(st[4 * n + i], (double)y));
+  d = dadd(d, dmul(st[5 * n + i], 1.0));
+  const int r = round2int(dmul(d, (double)pm.dis_scale));
+  (v == 0 ? dis0 : dis1)[i] = (uint8_t)min(max(r, 0), 255);  // saturate_cast<uchar>
+}
+
+// ---------------------------------------------------------- post-processing
+// LeftRightCheck (:347-369)
+__global__ void k_pp_lrcheck(PmDev pm, const uint8_t* dis0, const uint8_t* dis1, int* valid0, int* valid1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= pm.w) return;
+  const uint8_t* cur = v == 0 ? dis0 : dis1;
+  const uint8_t* oth = v == 0 ? dis1 : dis0;
+  const size_t row = (size_t)y * pm.w;
+  int ok = 0;
+  const double cur_dis = ddiv(dmul((double)cur[row + x], 1.0), (double)pm.dis_scale);
+  const int other_x = x + (2 * v - 1) * round2int(cur_dis);
+  if (other_x >= 0 && other_x < pm.w) {
+    const double other_dis = ddiv(dmul((double)oth[row + other_x], 1.0), (double)pm.dis_scale);
+    if (fabs(dsub(cur_dis, other_dis)) <= 0.5 && cur_dis > 0.0) ok = 1;
+  }
+  (v == 0 ? valid0 : valid1)[row + x] = ok;
+}
+// FillInvalid (:370-428): thread per pixel, scans its row for the nearest
+// valid pixel on each side (valid flags are not modified by this stage).
+__global__ void k_pp_fill(PmDev pm, uint8_t* dis0, uint8_t* dis1, const int* valid0, const int* valid1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, v = blockIdx.z;
+  if (x >= pm.w) return;
+  const int* yv = (v == 0 ? valid0 : valid1) + (size_t)y * pm.w;
+  if (yv[x]) return;
+  uint8_t* out = (v == 0 ? dis0 : dis1) + (size_t)y * pm.w;
+  int l = x, r = x;
+  while (l >= 0 && !yv[l]) --l;
+  while (r < pm.w && !yv[r]) ++r;
+  const size_t n = (size_t)pm.w * pm.h;
+  const double* st = pm.st[v];
+  auto disp_of = [&](int px) {
+    const size_t i = (size_t)y * pm.w + px;
+    double d = 0.0;
+    d = dadd(d, dmul(st[3 * n + i], (double)x));
+    d = dadd(d, dmul(st[4 * n + i], (double)y));
+    d = dadd(d, dmul(st[5 * n + i], 1.0));
+    return d;
+  };
+  const bool lf = l >= 0, rf = r < pm.w;
+  double d;
+  if (lf && rf) {
+    const double ld = disp_of(l), rd = disp_of(r);
+    d = ld <= rd ? ld : rd;
+  } else if (lf) d = disp_of(l);
+  else if (rf) d = disp_of(r);
+  else return;
+  out[x] = (uint8_t)min(max(pm.dis_scale * round2int(d), 0), 255);
+}
+// WeightedMedian (:430-506): thread per invalid pixel, 256-bin f64 histogram
+// in shared memory.  Only VALID neighbours contribute and valid pixels are
+// never rewritten, so reading `dis` while other threads update invalid pixels
+// is order-free; we still read from a snapshot to keep it race-free.
+__global__ void __launch_bounds__(16) k_pp_wmedian(PmDev pm, int v, const uint8_t* __restrict__ bgr,
+                                                   const uint8_t* __restrict__ dis_in, uint8_t* dis_out,
+                                                   const int* __restrict__ valid, const double* __restrict__ lut_w,
+                                                   int half_wnd) {
+  __shared__ double hist[16][257];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= pm.w) return;
+  const size_t row = (size_t)y * pm.w;
+  if (valid[row + x]) return;
+  double* hs = hist[threadIdx.x];
+  for (int d = 0; d < 256; ++d) hs[d] = 0.0;
+  const uint8_t* p = bgr + (row + x) * 3;
+  double sum_wgt = 0.0;
+  for (int wy = -half_wnd; wy <= half_wnd; ++wy) {
+    const int qy = y + wy;
+    if (qy < 0 || qy >= pm.h) continue;
+    for (int wx = -half_wnd; wx <= half_wnd; ++wx) {
+      const int qx = x + wx;
+      if (qx < 0 || qx >= pm.w) continue;
+      const size_t qi = (size_t)qy * pm.w + qx;
+      if (!valid[qi]) continue;
+      const uint8_t* q = bgr + qi * 3;
+      const int diff = abs((int)p[0] - q[0]) + abs((int)p[1] - q[1]) + abs((int)p[2] - q[2]);
+      const double wgt = lut_w[diff];
+      hs[dis_in[qi]] = dadd(hs[dis_in[qi]], wgt);
+      sum_wgt = dadd(sum_wgt, wgt);
+    }
+  }
+  const double median_wgt = ddiv(sum_wgt, 2.0);
+  double acc = 0.0;
+  int median = 0;
+  for (int d = 0; d < 256; ++d) {
+    acc = dadd(acc, hs[d]);
+    if (acc >= median_wgt) { median = d; break; }
+  }
+  if (median_wgt > 0.0) dis_out[row + x] = (uint8_t)median;
+}
+
+// -------------------------------------------------------------------- host
+static PmDev pm_dev(const cspm_pm* pm) {
+  PmDev d;
+  d.w = pm->w; d.h = pm->h; d.max_dis = pm->max_dis; d.n_ref = pm->n_ref; d.dis_scale = pm->dis_scale;
+  d.seed = pm->seed;
+  d.st[0] = pm->st[0]; d.st[1] = pm->st[1];
+  return d;
+}
+
+static void check_pair(const cspm_pm* pm, const cspm_pc* pc) {
+  CSPM_REQUIRE(pm, "null patch match handle");
+  CSPM_REQUIRE(pc, "null plane cost");
+  CSPM_REQUIRE(pc->device == pm->device, "plane cost and patch match live on different devices");
+  CSPM_REQUIRE(pc->dims[0][0] == pm->w && pc->dims[0][1] == pm->h, "plane cost and patch match image sizes differ");
+}
+
+static void run_init(cspm_pm* pm, const cspm_pc* pc) {
+  dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
+  k_init<<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
+  pm->stats.kernel_launches++;
+  pm->stats.plane_evals += 2ull * pm->w * pm->h;
+  pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
+}
+
+static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
+  k_refine<<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  pm->stats.kernel_launches++;
+  pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
+  pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
+}
+
+static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  const int rev = (iter % 2 == 0) ? 0 : 1;
+  const int wnd = 2 * pc->dev.half_wnd + 1;
+  const size_t smem = sizeof(double) * (kLutW + kLutC + 2 * (size_t)wnd * wnd);
+  const PmDev d = pm_dev(pm);
+  for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
+    const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
+    dim3 g(u_hi - u_lo + 1, 2);
+    k_spatial_diag<<<g, 128, smem, pm->stream>>>(pc->dev, d, diag, u_lo, rev);
+    pm->stats.kernel_launches++;
+  }
+  // evaluations: every pixel with an x-neighbour + every pixel with a y-neighbour, both views
+  const uint64_t ev = 2ull * ((uint64_t)(pm->w - 1) * pm->h + (uint64_t)pm->w * (pm->h - 1));
+  pm->stats.plane_evals += ev;
+  // tap count: whole-image totals minus the first scan column / row (mirror-symmetric)
+  pm->stats.window_taps += (uint64_t)((double)pc->taps_per_image_eval * ((double)ev / ((double)pm->w * pm->h)));
+}
+
+static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  const int rev = (iter % 2 == 0) ? 0 : 1;
+  const PmDev d = pm_dev(pm);
+  const size_t n = (size_t)pm->w * pm->h;
+  for (int v = 0; v < 2; ++v) {
+    k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
+    dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8);
+    k_view_eval<<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    dim3 g1((pm->w + 127) / 128, pm->h);
+    k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
+    k_view_commit<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->win);
+    pm->stats.kernel_launches += 4;
+    pm->stats.plane_evals += n;
+  }
+}
+
+static void run_plane2disp(cspm_pm* pm) {
+  dim3 g((pm->w + 127) / 128, pm->h, 2);
+  k_plane2disp<<<g, 128, 0, pm->stream>>>(pm_dev(pm), pm->dis[0], pm->dis[1]);
+  pm->stats.kernel_launches++;
+}
+
+static void run_postproc(cspm_pm* pm, const cspm_pc* pc) {
+  const PmDev d = pm_dev(pm);
+  dim3 g((pm->w + 127) / 128, pm->h, 2);
+  k_pp_lrcheck<<<g, 128, 0, pm->stream>>>(d, pm->dis[0], pm->dis[1], pm->valid[0], pm->valid[1]);
+  k_pp_fill<<<g, 128, 0, pm->stream>>>(d, pm->dis[0], pm->dis[1], pm->valid[0], pm->valid[1]);
+  pm->stats.kernel_launches += 2;
+  const size_t n = (size_t)pm->w * pm->h;
+  for (int v = 0; v < 2; ++v) {
+    CSPM_CUDA(cudaMemcpyAsync(pm->dis_tmp, pm->dis[v], n, cudaMemcpyDeviceToDevice, pm->stream));
+    dim3 g2((pm->w + 15) / 16, pm->h);
+    // WeightedMedian(valid, 35, WMF_GAMMA) — WMF_GAMMA == WGT_GAMMA == 10, same exp table
+    k_pp_wmedian<<<g2, 16, 0, pm->stream>>>(d, v, pm->d_bgr[v], pm->dis_tmp, pm->dis[v], pm->valid[v], pc->dev.lut_w, 35 / 2);
+    pm->stats.kernel_launches++;
+  }
+}
+
+static void sync_taps(cspm_pm* pm) {
+  unsigned long long t = 0;
+  CSPM_CUDA(cudaMemcpyAsync(&t, pm->tap_counter, sizeof(t), cudaMemcpyDeviceToHost, pm->stream));
+  CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  pm->stats.window_taps += t;
+  CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(t), pm->stream));
+}
+
+}  // namespace cspm
+
+using namespace cspm;
+
+extern "C" {
+
+cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis, int dis_scale,
+                          uint64_t seed, int schedule, int device) {
+  return guard_ptr<cspm_pm>([&]() -> cspm_pm* {
+    CSPM_REQUIRE(l && r, "null image pointer");
+    CSPM_REQUIRE(w > 0 && h > 0 && stride >= 3 * w, "bad image geometry");
+    CSPM_REQUIRE(max_dis >= 1 && dis_scale >= 1, "max_dis and dis_scale must be >= 1");
+    if (schedule != CSPM_SCHEDULE_RASTER) throw Error(CSPM_EUNSUPPORTED, "only CSPM_SCHEDULE_RASTER is implemented");
+    use_device(device);
+    cspm_pm* pm = new cspm_pm();
+    try {
+      pm->device = device;
+      pm->w = w; pm->h = h; pm->max_dis = max_dis; pm->dis_scale = dis_scale; pm->schedule = schedule;
+      pm->seed = seed;
+      int nr = 0;
+      for (double z = max_dis / 2.0; z >= 0.1; z /= 2.0) ++nr;  // kZStopThres_ = 0.1
+      pm->n_ref = nr;
+      CSPM_CUDA(cudaStreamCreateWithFlags(&pm->stream, cudaStreamNonBlocking));
+      const size_t n = (size_t)w * h;
+      for (int v = 0; v < 2; ++v) {
+        pm->st[v] = pm->arena.alloc<double>(7 * n);
+        pm->dis[v] = pm->arena.alloc<uint8_t>(n);
+        pm->d_bgr[v] = pm->arena.alloc<uint8_t>(3 * n);
+        pm->valid[v] = pm->arena.alloc<int>(n);
+        CSPM_CUDA(cudaMemsetAsync(pm->dis[v], 0, n, pm->stream));                  // Mat::zeros (:15)
+        CSPM_CUDA(cudaMemsetAsync(pm->st[v], 0, sizeof(double) * 6 * n, pm->stream));  // Plane() = zeros
+        CSPM_CUDA(cudaMemcpy2DAsync(pm->d_bgr[v], (size_t)3 * w, v == 0 ? l : r, (size_t)stride, (size_t)3 * w, h,
+                                    cudaMemcpyHostToDevice, pm->stream));
+      }
+      // min_cost_ = kDoubleMax (:25)
+      std::vector<double> mx(n, 1.7976931348623157e308);
+      for (int v = 0; v < 2; ++v)
+        CSPM_CUDA(cudaMemcpyAsync(pm->st[v] + 6 * n, mx.data(), sizeof(double) * n, cudaMemcpyHostToDevice, pm->stream));
+      pm->cand_cost = pm->arena.alloc<double>(n);
+      pm->cand_tx = pm->arena.alloc<int>(n);
+      pm->tmin = pm->arena.alloc<unsigned long long>(n);
+      pm->win = pm->arena.alloc<unsigned int>(n);
+      pm->dis_tmp = pm->arena.alloc<uint8_t>(n);
+      pm->tap_counter = pm->arena.alloc<unsigned long long>(1);
+      CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(unsigned long long), pm->stream));
+      CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+      return pm;
+    } catch (...) {
+      pm->arena.release();
+      if (pm->stream) cudaStreamDestroy(pm->stream);
+      delete pm;
+      throw;
+    }
+  });
+}
+
+void cspm_pm_destroy(cspm_pm_t* pm) {
+  if (!pm) return;
+  cudaSetDevice(pm->device);
+  if (pm->stream) {
+    cudaStreamSynchronize(pm->stream);
+    cudaStreamDestroy(pm->stream);
+  }
+  pm->arena.release();
+  delete pm;
+}
+
+int cspm_pm_n_ref(const cspm_pm_t* pm) { return pm ? pm->n_ref : CSPM_EINVAL; }
+
+int cspm_pm_stage(cspm_pm_t* pm, int stage, int iter, const cspm_pc_t* pc) {
+  return guard([&] {
+    CSPM_REQUIRE(pm, "null patch match handle");
+    CSPM_REQUIRE(stage >= 0 && stage <= 5 && iter >= 0, "bad stage / iteration");
+    if (stage != CSPM_STAGE_PLANE2DISP) check_pair(pm, pc);
+    use_device(pm->device);
+    switch (stage) {
+      case CSPM_STAGE_INIT: run_init(pm, pc); break;
+      case CSPM_STAGE_SPATIAL: run_spatial(pm, pc, iter); break;
+      case CSPM_STAGE_VIEW: run_view(pm, pc, iter); break;
+      case CSPM_STAGE_REFINE: run_refine(pm, pc, iter); break;
+      case CSPM_STAGE_PLANE2DISP: run_plane2disp(pm); break;
+      case CSPM_STAGE_POSTPROC: run_postproc(pm, pc); break;
+    }
+    CSPM_CUDA(cudaGetLastError());
+    sync_taps(pm);
+  });
+}
+
+int cspm_pm_patchmatch(cspm_pm_t* pm, int iter_num, const cspm_pc_t* pc, int use_pp) {
+  return guard([&] {
+    check_pair(pm, pc);
+    CSPM_REQUIRE(iter_num >= 0, "negative iteration count");
+    use_device(pm->device);
+    // stage timing: events on the handle's stream
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_stage;
+    auto mark = [&](int stage) {
+      cudaEvent_t e;
+      CSPM_CUDA(cudaEventCreate(&e));
+      CSPM_CUDA(cudaEventRecord(e, pm->stream));
+      ev.push_back(e);
+      ev_stage.push_back(stage);
+    };
+    mark(CSPM_STAGE_INIT);
+    run_init(pm, pc);
+    for (int i = 0; i < iter_num; ++i) {
+      mark(CSPM_STAGE_SPATIAL);
+      run_spatial(pm, pc, i);
+      mark(CSPM_STAGE_VIEW);
+      run_view(pm, pc, i);
+      mark(CSPM_STAGE_REFINE);
+      run_refine(pm, pc, i);
+    }
+    mark(CSPM_STAGE_PLANE2DISP);
+    run_plane2disp(pm);
+    if (use_pp) {
+      mark(CSPM_STAGE_POSTPROC);
+      run_postproc(pm, pc);
+    }
+    mark(-1);
+    CSPM_CUDA(cudaGetLastError());
+    sync_taps(pm);
+    for (int s = 0; s < 6; ++s) pm->stage_ms[s] = 0.f;
+    for (size_t k = 0; k + 1 < ev.size(); ++k) {
+      float ms = 0.f;
+      CSPM_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      pm->stage_ms[ev_stage[k]] += ms;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  });
+}
+
+int cspm_pm_get_dis(const cspm_pm_t* pm, int view, uint8_t* out, int out_stride) {
+  return guard([&] {
+    CSPM_REQUIRE(pm && out && (view == 0 || view == 1) && out_stride >= pm->w, "bad argument");
+    use_device(pm->device);
+    CSPM_CUDA(cudaMemcpy2DAsync(out, (size_t)out_stride, pm->dis[view], (size_t)pm->w, (size_t)pm->w, pm->h,
+                                cudaMemcpyDeviceToHost, pm->stream));
+    CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  });
+}
+int cspm_pm_set_dis(cspm_pm_t* pm, int view, const uint8_t* in, int in_stride) {
+  return guard([&] {
+    CSPM_REQUIRE(pm && in && (view == 0 || view == 1) && in_stride >= pm->w, "bad argument");
+    use_device(pm->device);
+    CSPM_CUDA(cudaMemcpy2DAsync(pm->dis[view], (size_t)pm->w, in, (size_t)in_stride, (size_t)pm->w, pm->h,
+                                cudaMemcpyHostToDevice, pm->stream));
+    CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  });
+}
+
+int cspm_pm_get_planes(const cspm_pm_t* pm, int view, double* normal, double* param, double* min_cost) {
+  return guard([&] {
+    CSPM_REQUIRE(pm && (view == 0 || view == 1), "bad argument");
+    use_device(pm->device);
+    const size_t n = (size_t)pm->w * pm->h;
+    std::vector<double> h(7 * n);
+    CSPM_CUDA(cudaMemcpyAsync(h.data(), pm->st[view], sizeof(double) * 7 * n, cudaMemcpyDeviceToHost, pm->stream));
+    CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        if (normal) normal[3 * i + k] = h[k * n + i];
+        if (param) param[3 * i + k] = h[(3 + k) * n + i];
+      }
+      if (min_cost) min_cost[i] = h[6 * n + i];
+    }
+  });
+}
+int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const double* param, const double* min_cost) {
+  return guard([&] {
+    CSPM_REQUIRE(pm && normal && param && min_cost && (view == 0 || view == 1), "bad argument");
+    use_device(pm->device);
+    const size_t n = (size_t)pm->w * pm->h;
+    std::vector<double> h(7 * n);
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        h[k * n + i] = normal[3 * i + k];
+        h[(3 + k) * n + i] = param[3 * i + k];
+      }
+      h[6 * n + i] = min_cost[i];
+    }
+    CSPM_CUDA(cudaMemcpyAsync(pm->st[view], h.data(), sizeof(double) * 7 * n, cudaMemcpyHostToDevice, pm->stream));
+    CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  });
+}
+
+void* cspm_pm_stream(const cspm_pm_t* pm) { return pm ? (void*)pm->stream : nullptr; }
+int cspm_pm_stats(const cspm_pm_t* pm, cspm_stats_t* out) {
+  if (!pm || !out) return CSPM_EINVAL;
+  *out = pm->stats;
+  return CSPM_OK;
+}
+int cspm_pm_stage_ms(const cspm_pm_t* pm, float* ms) {
+  if (!pm || !ms) return CSPM_EINVAL;
+  for (int s = 0; s < 6; ++s) ms[s] = pm->stage_ms[s];
+  return CSPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""GPU parity: libcspm_b200.so (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Bar: BIT-EXACT on every output — uint8 disparities,
+f64 plane parameters, f64 aggregated costs (tolerance 0): the kernels execute
+the reference's f64 operations in the reference's order without FMA
+contraction, so there is nothing to tolerate."""
+import numpy as np
+import pytest
+
+import orc
+from crossscalepatchmatch_b200.synth import make_pair
+
+pytestmark = pytest.mark.gpu
+
+W, H, D = 96, 64, 24
+
+
+@pytest.fixture(scope="module")
+def cspm():
+    import crossscalepatchmatch_b200 as c
+
+    assert c.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return c
+
+
+@pytest.fixture(scope="module")
+def pair():
+    l, r, gt = make_pair(W, H, D, 0xC5B20000)
+    return l, r
+
+
+def _queries(rng, w, h, d, n):
+    x = rng.integers(0, w, n)
+    y = rng.integers(0, h, n)
+    # force border / corner pixels in
+    x[:8] = [0, w - 1, 0, w - 1, 1, w - 2, w // 2, 0]
+    y[:8] = [0, 0, h - 1, h - 1, 1, h - 2, 0, h // 2]
+    v = rng.integers(0, 2, n)
+    nm = rng.normal(size=(n, 3))
+    nm /= np.linalg.norm(nm, axis=1)[:, None]
+    nm[8:16] = [0, 0, 1]            # fronto-parallel
+    nm[16:20, 2] = 1e-12            # |nz| < eps guard in update_param
+    nm[20:24] = [0, 0, -1]          # negative nz
+    z = rng.uniform(-2, d + 2, n)   # includes invalid disparities
+    z[8:16] = np.arange(1, 9)       # integer disparities: fw == 1
+    pt = np.stack([x, y, z], 1).astype(np.float64)
+    return x, y, nm, pt, v
+
+
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (2, 0.3), (3, 0.3), (5, 0.3), (3, 0.0)])
+def test_plane_cost_info_and_costs(cspm, orc_lib, pair, S, lam):
+    l, r = pair
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam)
+    pg = cspm.PreSSPC(l, r, D, 35, cc) if S == 0 else cspm.PreCSPC(l, r, D, 35, S, cc, lam)
+    wo, mo, do = po.info()
+    wg, mg, dg = pg.info()
+    assert np.array_equal(do, dg)
+    assert np.array_equal(mo, mg), (mo, mg)
+    assert np.array_equal(wo, wg), (wo, wg)
+    for s in range(max(S, 1)):
+        for v in (0, 1):
+            assert np.array_equal(po.scale_image(s, v), pg.scale_image(s, v)), f"pyramid level {s} view {v}"
+    x, y, nm, pt, v = _queries(np.random.default_rng(1), W, H, D, 4000)
+    co = po.get_plane_cost(x, y, nm, pt, v)
+    cg = pg.GetPlaneCostBatch(x, y, nm, pt, v)
+    bad = np.flatnonzero(co != cg)
+    assert bad.size == 0, f"{bad.size} costs differ, first {bad[:5]}: {co[bad[:5]]} vs {cg[bad[:5]]}"
+
+
+def test_scalar_get_plane_cost(cspm, orc_lib, pair):
+    l, r = pair
+    pg = cspm.PreSSPC(l, r, D, 35, cspm.GetCCType("GRD"))
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, 0, 0.0)
+    pl = cspm.Plane((0.0, 0.0, 1.0), (10.0, 12.0, 5.0))
+    got = pg.GetPlaneCost(10, 12, pl, cspm.kLeft)
+    want = po.get_plane_cost([10], [12], [[0, 0, 1.0]], [[10, 12, 5.0]], [0])[0]
+    assert got == want
+
+
+@pytest.mark.parametrize("right", [0, 1])
+def test_build_cv(cspm, orc_lib, pair, right):
+    l, r = pair
+    lrgb = l[..., ::-1].astype(np.float64)
+    rrgb = r[..., ::-1].astype(np.float64)
+    cc = cspm.GrdCC()
+    got = cc.buildRightCV(lrgb, rrgb, D + 1) if right else cc.buildCV(lrgb, rrgb, D + 1)
+    want = orc_lib.build_cv("GRD", lrgb, rrgb, D + 1, right)
+    assert np.array_equal(got, want)
+
+
+def _same_state(a, b, what):
+    for view in (0, 1):
+        for name, x, y in zip(("normal", "param", "min_cost"), a.planes(view), b.planes(view)):
+            bad = np.argwhere(x != y)
+            assert bad.size == 0, f"{what}: view {view} {name}: {len(bad)} mismatches, first at {bad[0]}: {x[tuple(bad[0])]} vs {y[tuple(bad[0])]}"
+
+
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (3, 0.3)])
+def test_stages_bit_exact(cspm, orc_lib, pair, S, lam):
+    """Drive the stages one by one; after each, GPU state must equal the oracle's
+    bit for bit (and is re-synchronised from the oracle so a failure is local)."""
+    l, r = pair
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam)
+    pg = cspm.PreSSPC(l, r, D, 35, cc) if S == 0 else cspm.PreCSPC(l, r, D, 35, S, cc, lam)
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=0x5EED)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=0x5EED)
+    assert mg.n_ref() == orc_lib.pm_n_ref(mo.h_)
+    mo.stage(orc.PatchMatch.INIT, 0, po)
+    mg.stage(cspm.STAGE_INIT, 0, pg)
+    _same_state(mo, mg, "init")
+    for it in range(2):
+        for so, sg, name in ((orc.PatchMatch.SPATIAL, cspm.STAGE_SPATIAL, "spatial"),
+                             (orc.PatchMatch.VIEW, cspm.STAGE_VIEW, "view"),
+                             (orc.PatchMatch.REFINE, cspm.STAGE_REFINE, "refine")):
+            mo.stage(so, it, po)
+            mg.stage(sg, it, pg)
+            _same_state(mo, mg, f"iter {it} {name}")
+    mo.stage(orc.PatchMatch.PLANE2DISP)
+    mg.stage(cspm.STAGE_PLANE2DISP)
+    for v in (0, 1):
+        assert np.array_equal(mo.dis(v), mg.dis(v))
+    mo.stage(orc.PatchMatch.POSTPROC, 0, po)
+    mg.stage(cspm.STAGE_POSTPROC, 0, pg)
+    for v in (0, 1):
+        assert np.array_equal(mo.dis(v), mg.dis(v)), "post-processing"
+
+
+@pytest.mark.parametrize("w,h,d,scale,S,lam,iters,pp", [
+    (80, 60, 16, 4, 0, 0.0, 3, False),
+    (80, 60, 16, 4, 3, 0.3, 2, True),
+    (37, 41, 9, 8, 2, 1.0, 2, True),     # odd sizes, window larger than the image at coarse scales
+    (130, 20, 40, 1, 0, 0.0, 1, False),  # wide, disparity range ~ image width: heavy wrap-around in view propagation
+])
+def test_full_patchmatch_bit_exact(cspm, orc_lib, w, h, d, scale, S, lam, iters, pp):
+    l, r, _ = make_pair(w, h, d, 0xC5B20000 + w)
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam)
+    pg = cspm.PreSSPC(l, r, d, 35, cc) if S == 0 else cspm.PreCSPC(l, r, d, 35, S, cc, lam)
+    mo = orc.PatchMatch(orc_lib, l, r, d, scale, seed=7)
+    mg = cspm.CSPatchMatch(l, r, d, scale, seed=7)
+    mo.patchmatch(iters, po, pp)
+    mg.PatchMatch(iters, pg, pp)
+    _same_state(mo, mg, "full run")
+    for v in (0, 1):
+        assert np.array_equal(mo.dis(v), mg.dis(v))
+    st = mg.stats()
+    evals_per_px = 1 + iters * (1 + mg.n_ref())
+    assert st["plane_evals"] == 2 * w * h * evals_per_px + iters * 2 * ((w - 1) * h + w * (h - 1))
+    assert st["kernel_launches"] > 0 and st["window_taps"] > 0
+
+
+def test_error_behaviour(cspm, pair):
+    l, r = pair
+    assert cspm.GetCCType("BSM") is None            # main.cc:47-54
+    with pytest.raises(cspm.CspmError):
+        cspm.PreSSPC(l, r, D, 35, None)              # NULL cc_method
+    with pytest.raises(cspm.CspmError):
+        cspm.PreSSPC(l.astype(np.float64), r, D, 35, cspm.GetCCType("GRD"))  # CV_Assert(CV_8UC3)
+    with pytest.raises(cspm.CspmError):
+        cspm.PreCSPC(l, r, D, 35, 1, cspm.GetCCType("GRD"), 0.3)  # scale_num >= 2 (pre_cs_pc.cc:93)
+    pg = cspm.PreSSPC(l, r, D, 35, cspm.GetCCType("GRD"))
+    with pytest.raises(cspm.CspmError):
+        pg.GetPlaneCostBatch([W], [0], [[0, 0, 1.0]], [[0, 0, 1.0]], [0])  # pixel outside the image
+    small = cspm.CSPatchMatch(l[:32, :32].copy(), r[:32, :32].copy(), D, 4)
+    with pytest.raises(cspm.CspmError):
+        small.PatchMatch(1, pg)                      # geometry mismatch
