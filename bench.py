@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 PatchMatch engine.
+
+Metric (BASELINE.json): Mpixel*disparities/s = W*H*max_dis / t / 1e6 per stereo
+pair on synthetic 1920x1080, max_dis=256 pairs, 3 PatchMatch iterations
+(configs[3]); t covers the region the reference times (main.cc:92-123):
+plane-cost construction + CSPatchMatch construction + PatchMatch(3, pc, false).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--use-cs] [--impl reference]
+
+One "step" = one stereo pair.  N>1: launched under torchrun, one rank per GPU,
+every rank works on its own pair (independent units, no data-path collective;
+"scaling": "weak"); NCCL is used only for the barrier and the max-over-ranks
+of the elapsed time.
+
+`value`  : device-resident inputs, CUDA events on the stream the library
+           launches on (PyTorch's current stream, injected through
+           cspm_set_thread_stream), one event pair per step, L2 flushed between
+           steps; max over ranks.
+`e2e`    : the same pair through the host-pointer API (pinned host images in,
+           two uint8 disparity maps out), wall clock with a device synchronise
+           on both sides, H2D/D2H inside the timed region.
+`roofline`: dominant kernel = the PlaneRefinement launch; achieved = 19 B x
+           border-clipped window taps of that launch / its CUDA-event duration
+           (SURVEY.md §8d no-reuse gather model), peak = MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own CPU code (oracle/_ref: unmodified reference
+           sources + OpenCV shim) or, if that .so is absent, the oracle port,
+           on a bounded crop of the same pair with all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_HD, H_HD, D_HD = 1920, 1080, 256
+ITERS = 3
+WND = 35
+BYTES_PER_TAP = 19  # 3 B guide pixel + 2 x 8 B cost samples (pre_ss_pc.cc:93,109-110)
+CPU_CROP = (240, 136)  # bounded CPU sample (w, h), same max_dis
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--use-cs", action="store_true", help="cross-scale plane cost (PreCSPC, S=3, lambda=0.3)")
+    ap.add_argument("--size", default=None, help="WxHxD override (debug only; the headline is 1920x1080x256)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    if args.size:
+        w, h, d = (int(v) for v in args.size.lower().split("x"))
+    else:
+        w, h, d = W_HD, H_HD, D_HD
+    name = f"synthetic {w}x{h} pair, max_dis={d}, {ITERS} PatchMatch iters, wnd=35, GRD, " + (
+        "cross-scale S=3 lambda=0.3" if args.use_cs else "single-scale") + ", use_pp=false"
+    return w, h, d, name
+
+
+# ---------------------------------------------------------------- CPU arms
+def cpu_run(l, r, d, use_cs, nthreads):
+    """One pass of the reference's timed region on the CPU; returns (seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+
+    if orc.ref_available():
+        lib, kind = orc.ref(), "reference"
+        lib.set_time_mode(1)  # time(NULL) constant within the run, like a real clock within one second
+    else:
+        lib, kind = orc.oracle(), "port"
+    t0 = time.perf_counter()
+    pc = orc.PlaneCost(lib, l, r, d, WND, 3 if use_cs else 0, 0.3 if use_cs else 0.0)
+    pm = orc.PatchMatch(lib, l, r, d, 1)
+    pm.patchmatch(ITERS, pc, False, nthreads)
+    t = time.perf_counter() - t0
+    pm.close()
+    pc.close()
+    return t, kind
+
+
+def cpu_sample(w, h, d, seed):
+    from crossscalepatchmatch_b200.synth import make_pair
+
+    cw, ch = min(CPU_CROP[0], w), min(CPU_CROP[1], h)
+    l, r, _ = make_pair(w, h, d, seed)
+    x0, y0 = (w - cw) // 2, (h - ch) // 2
+    return np.ascontiguousarray(l[y0:y0 + ch, x0:x0 + cw]), np.ascontiguousarray(r[y0:y0 + ch, x0:x0 + cw]), cw, ch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    w, h, d, name = workload(args)
+    from crossscalepatchmatch_b200.synth import SEED_BASE
+
+    l, r, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
+    cores = os.cpu_count() or 1
+    kind = "port"
+    for _ in range(min(args.warmup, 1)):  # one CPU warm-up pass is plenty (no JIT, no caches to prime)
+        cpu_run(l, r, d, args.use_cs, cores)
+    ts = []
+    for _ in range(args.steps):
+        t, kind = cpu_run(l, r, d, args.use_cs, cores)
+        ts.append(t)
+    total = sum(ts)
+    value = cw * ch * d * args.steps / total / 1e6
+    sample = f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline ({ITERS} iters)"
+    line = {
+        "impl": "reference", "metric": "Mpixel*disparities/s", "value": value, "unit": "Mpixel*disp/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------- clock sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import crossscalepatchmatch_b200 as c
+    from crossscalepatchmatch_b200.synth import SEED_BASE, make_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert torch.cuda.is_available() and c.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w, h, d, name = workload(args)
+
+    # this rank's pair (config C4 seed + pair index); pinned host copies for the e2e leg
+    l, r, _ = make_pair(w, h, d, SEED_BASE + 3 + rank)
+    hl = torch.from_numpy(l).pin_memory()
+    hr = torch.from_numpy(r).pin_memory()
+    dl, dr = hl.to(dev), hr.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    stream = torch.cuda.current_stream()
+    c.set_thread_stream(stream.cuda_stream)  # library launches on torch's current stream
+    cc = c.GetCCType("GRD")
+    S, lam = (3, 0.3) if args.use_cs else (0, 0.0)
+
+    def make_pc(lp, rp, dev_ptrs):
+        kw = {"device": local}
+        if dev_ptrs:
+            kw["device_ptrs"] = ((lp.data_ptr(), w, h, 3 * w), (rp.data_ptr(), w, h, 3 * w))
+            lp = rp = None
+        else:
+            lp, rp = lp.numpy(), rp.numpy()
+        if S == 0:
+            return c.PreSSPC(lp, rp, d, WND, cc, **kw)
+        return c.PreCSPC(lp, rp, d, WND, S, cc, lam, **kw)
+
+    launches = {"n": 0}
+    last = {}
+
+    def step_device():
+        """reference's timed region with inputs resident in HBM"""
+        pc = make_pc(dl, dr, True)
+        pm = c.CSPatchMatch(None, None, d, 1, seed=0x5EED, device=local,
+                            device_ptrs=((dl.data_ptr(), w, h, 3 * w), (dr.data_ptr(), w, h, 3 * w)))
+        pm.PatchMatch(ITERS, pc, False)
+        launches["n"] += pc.stats()["kernel_launches"] + pm.stats()["kernel_launches"]
+        last.update(stage_ms=pm.stage_ms(), taps_eval=pc.taps_per_image_eval(), n_ref=pm.n_ref(), stats=pm.stats())
+        return pc, pm
+
+    def step_e2e():
+        pc = make_pc(hl, hr, False)
+        pm = c.CSPatchMatch(hl.numpy(), hr.numpy(), d, 1, seed=0x5EED, device=local)
+        pm.PatchMatch(ITERS, pc, False)
+        return pm.dis(c.kLeft), pm.dis(c.kRight)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    launches["n"] = 0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    refine_ms = []
+    for k in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (outside the timed region)
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        refine_ms.append(last["stage_ms"][c.STAGE_REFINE] / ITERS)
+    barrier()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    gpu_launches = launches["n"]
+
+    # end-to-end leg: host buffers in, disparity maps out
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+
+    if rank == 0:
+        units = w * h * d * args.steps * world
+        value = units / t_dev / 1e6
+        e2e = units / t_e2e / 1e6
+        # roofline of the dominant kernel (k_refine, one launch per iteration, both views)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        taps_launch = 2 * last["n_ref"] * last["taps_eval"]
+        ms = float(np.mean(refine_ms))
+        achieved = BYTES_PER_TAP * taps_launch / (ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("cs" if args.use_cs else "ss")
+        stage_ms = dict(zip(["init", "spatial", "view", "refine", "plane2disp", "postproc"], last["stage_ms"]))
+        line = {
+            "metric": "Mpixel*disparities/s", "value": value, "unit": "Mpixel*disp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "pairs_per_gpu_per_step": 1, "sharding": "one stereo pair per GPU, no data-path collective",
+                       "schedule": "raster (bit-exact reference order)", "l2": "flushed between timed steps (256 MiB write)"},
+            "e2e": {"value": e2e, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 4 * w * h * 3, "d2h_bytes_per_step": 2 * w * h,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_refine", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_TAP * taps_launch, "launch_ms": ms,
+                         "model": "no-reuse gather, 19 B per border-clipped window tap (SURVEY.md 8d)"},
+            "stage_ms": stage_ms,
+            "window_taps_per_step": int(last["stats"]["window_taps"]),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cl, cr, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
+            cores = os.cpu_count() or 1
+            t, kind = cpu_run(cl, cr, d, args.use_cs, cores)
+            line["cpu_baseline"] = {"value": cw * ch * d / t / 1e6, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind,
+                                    "sample": f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline, 1 pass ({t:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

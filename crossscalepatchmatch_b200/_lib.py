@@ -35,6 +35,9 @@ SIGNATURES = {
     "cspm_last_error": (C.c_char_p, []),
     "cspm_device_count": (C.c_int, []),
     "cspm_version": (C.c_char_p, []),
+    "cspm_set_thread_stream": (None, [C.c_void_p]),
+    "cspm_pc_taps_per_image_eval": (C.c_uint64, [C.c_void_p]),
+    "cspm_pm_create_dev": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]),
     "cspm_cc_create": (C.c_void_p, [C.c_char_p]),
     "cspm_cc_destroy": (None, [C.c_void_p]),
     "cspm_cc_name": (C.c_char_p, [C.c_void_p]),

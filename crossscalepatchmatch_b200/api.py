@@ -35,6 +35,11 @@ def _img(a) -> np.ndarray:
     return a
 
 
+def set_thread_stream(cuda_stream: int | None):
+    """Handles created by this thread afterwards launch on `cuda_stream` (a raw cudaStream_t)."""
+    dll.cspm_set_thread_stream(C.c_void_p(cuda_stream) if cuda_stream else None)
+
+
 class Plane:
     """plane.h:12-48 — unit normal + point, derived (a, b, c)."""
 
@@ -149,6 +154,9 @@ class IPlaneCost:
     def stream(self) -> int:
         return dll.cspm_pc_stream(self._h) or 0
 
+    def taps_per_image_eval(self) -> int:
+        return int(dll.cspm_pc_taps_per_image_eval(self._h))
+
     def stats(self):
         s = _lib.Stats()
         check(dll.cspm_pc_stats(self._h, C.byref(s)))
@@ -199,13 +207,15 @@ class PreCSPC(IPlaneCost):
 class CSPatchMatch:
     """cs_patchmatch.h:16-147 — CSPatchMatch(l_img, r_img, max_dis, dis_scale)."""
 
-    def __init__(self, l_img, r_img, max_dis, dis_scale, seed=0x5EED, schedule=_lib.SCHEDULE_RASTER, device=0):
-        l, r = _img(l_img), _img(r_img)
-        if l.shape != r.shape or l.strides != r.strides:
+    def __init__(self, l_img, r_img, max_dis, dis_scale, seed=0x5EED, schedule=_lib.SCHEDULE_RASTER, device=0,
+                 device_ptrs=None):
+        lp, w, h, stride, self._kl = _ptr_and_geom(l_img, device_ptrs[0] if device_ptrs else None)
+        rp, w2, h2, stride2, self._kr = _ptr_and_geom(r_img, device_ptrs[1] if device_ptrs else None)
+        if (w, h, stride) != (w2, h2, stride2):
             raise CspmError(_lib.EINVAL, "left/right geometry differs")
-        self.h, self.w = l.shape[:2]
-        self._h = dll.cspm_pm_create(C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data), self.w, self.h,
-                                     l.strides[0], max_dis, dis_scale, seed, schedule, device)
+        self.h, self.w = h, w
+        fn = dll.cspm_pm_create_dev if device_ptrs else dll.cspm_pm_create
+        self._h = fn(lp, rp, w, h, stride, max_dis, dis_scale, seed, schedule, device)
         if not self._h:
             raise CspmError(_lib.ENODEV, _lib.last_error())
 

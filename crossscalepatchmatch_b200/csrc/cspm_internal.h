@@ -61,6 +61,9 @@ T* guard_ptr(F&& f) {
 // Selects the device for the current thread and checks it exists.  This is
 // where a box without a GPU fails loudly (no CPU fallback anywhere).
 void use_device(int device);
+// Stream for a new handle: the thread's injected stream (cspm_set_thread_stream)
+// or a fresh private one.  *owned tells the destructor whether to destroy it.
+cudaStream_t acquire_stream(bool* owned);
 
 struct DeviceArena {
   std::vector<void*> ptrs;
@@ -87,6 +90,7 @@ struct cspm_cc {
 struct cspm_pc {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   cspm::PcDev dev{};
   int wnd_size = 35;
   int scale_num = 1;  // 1 for PreSSPC
@@ -103,6 +107,7 @@ struct cspm_pc {
 struct cspm_pm {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   int w = 0, h = 0, max_dis = 0, dis_scale = 1, schedule = 0, n_ref = 0;
   uint64_t seed = 0;
   double* st[2] = {nullptr, nullptr};  // 7 planes of w*h: nx ny nz a b c cost

@@ -365,6 +365,11 @@ __global__ void __launch_bounds__(16) k_pp_wmedian(PmDev pm, int v, const uint8_
   if (median_wgt > 0.0) dis_out[row + x] = (uint8_t)median;
 }
 
+__global__ void k_fill_f64(double* p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // -------------------------------------------------------------------- host
 static PmDev pm_dev(const cspm_pm* pm) {
   PmDev d;
@@ -467,8 +472,8 @@ using namespace cspm;
 
 extern "C" {
 
-cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis, int dis_scale,
-                          uint64_t seed, int schedule, int device) {
+static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, int w, int h, int stride, int max_dis,
+                            int dis_scale, uint64_t seed, int schedule, int device) {
   return guard_ptr<cspm_pm>([&]() -> cspm_pm* {
     CSPM_REQUIRE(l && r, "null image pointer");
     CSPM_REQUIRE(w > 0 && h > 0 && stride >= 3 * w, "bad image geometry");
@@ -483,7 +488,7 @@ cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int 
       int nr = 0;
       for (double z = max_dis / 2.0; z >= 0.1; z /= 2.0) ++nr;  // kZStopThres_ = 0.1
       pm->n_ref = nr;
-      CSPM_CUDA(cudaStreamCreateWithFlags(&pm->stream, cudaStreamNonBlocking));
+      pm->stream = acquire_stream(&pm->own_stream);
       const size_t n = (size_t)w * h;
       for (int v = 0; v < 2; ++v) {
         pm->st[v] = pm->arena.alloc<double>(7 * n);
@@ -493,12 +498,11 @@ cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int 
         CSPM_CUDA(cudaMemsetAsync(pm->dis[v], 0, n, pm->stream));                  // Mat::zeros (:15)
         CSPM_CUDA(cudaMemsetAsync(pm->st[v], 0, sizeof(double) * 6 * n, pm->stream));  // Plane() = zeros
         CSPM_CUDA(cudaMemcpy2DAsync(pm->d_bgr[v], (size_t)3 * w, v == 0 ? l : r, (size_t)stride, (size_t)3 * w, h,
-                                    cudaMemcpyHostToDevice, pm->stream));
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, pm->stream));
+        // min_cost_ = kDoubleMax (:25)
+        k_fill_f64<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(pm->st[v] + 6 * n, n, 1.7976931348623157e308);
+        pm->stats.kernel_launches++;
       }
-      // min_cost_ = kDoubleMax (:25)
-      std::vector<double> mx(n, 1.7976931348623157e308);
-      for (int v = 0; v < 2; ++v)
-        CSPM_CUDA(cudaMemcpyAsync(pm->st[v] + 6 * n, mx.data(), sizeof(double) * n, cudaMemcpyHostToDevice, pm->stream));
       pm->cand_cost = pm->arena.alloc<double>(n);
       pm->cand_tx = pm->arena.alloc<int>(n);
       pm->tmin = pm->arena.alloc<unsigned long long>(n);
@@ -510,20 +514,26 @@ cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int 
       return pm;
     } catch (...) {
       pm->arena.release();
-      if (pm->stream) cudaStreamDestroy(pm->stream);
+      if (pm->stream && pm->own_stream) cudaStreamDestroy(pm->stream);
       delete pm;
       throw;
     }
   });
 }
+cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis, int dis_scale,
+                          uint64_t seed, int schedule, int device) {
+  return pm_create(l, r, false, w, h, stride, max_dis, dis_scale, seed, schedule, device);
+}
+cspm_pm_t* cspm_pm_create_dev(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis, int dis_scale,
+                              uint64_t seed, int schedule, int device) {
+  return pm_create(l, r, true, w, h, stride, max_dis, dis_scale, seed, schedule, device);
+}
 
 void cspm_pm_destroy(cspm_pm_t* pm) {
   if (!pm) return;
   cudaSetDevice(pm->device);
-  if (pm->stream) {
-    cudaStreamSynchronize(pm->stream);
-    cudaStreamDestroy(pm->stream);
-  }
+  cudaStreamSynchronize(pm->stream);
+  if (pm->own_stream) cudaStreamDestroy(pm->stream);
   pm->arena.release();
   delete pm;
 }

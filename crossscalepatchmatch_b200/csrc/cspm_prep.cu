@@ -15,6 +15,19 @@ namespace cspm {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
+static thread_local cudaStream_t g_thread_stream = nullptr;
+static thread_local bool g_thread_stream_set = false;
+cudaStream_t acquire_stream(bool* owned) {
+  if (g_thread_stream_set) {
+    *owned = false;
+    return g_thread_stream;
+  }
+  cudaStream_t st;
+  CSPM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *owned = true;
+  return st;
+}
+
 void use_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -250,7 +263,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     pc->device = device;
     pc->wnd_size = wnd_size;
     pc->scale_num = cross_scale ? scale_num : 1;
-    CSPM_CUDA(cudaStreamCreateWithFlags(&pc->stream, cudaStreamNonBlocking));
+    pc->stream = acquire_stream(&pc->own_stream);
     cudaStream_t st = pc->stream;
     PcDev& D = pc->dev;
     D.cc_kind = cc->kind;
@@ -359,7 +372,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     return pc;
   } catch (...) {
     pc->arena.release();
-    if (pc->stream) cudaStreamDestroy(pc->stream);
+    if (pc->stream && pc->own_stream) cudaStreamDestroy(pc->stream);
     delete pc;
     throw;
   }
@@ -381,6 +394,12 @@ int cspm_device_count(void) {
   }
   return n;
 }
+
+void cspm_set_thread_stream(void* cuda_stream) {
+  g_thread_stream = (cudaStream_t)cuda_stream;
+  g_thread_stream_set = cuda_stream != nullptr;
+}
+uint64_t cspm_pc_taps_per_image_eval(const cspm_pc_t* pc) { return pc ? pc->taps_per_image_eval : 0; }
 
 cspm_cc_t* cspm_cc_create(const char* name) {
   if (!name) {
@@ -450,10 +469,8 @@ cspm_pc_t* cspm_pc_create_cs_dev(const uint8_t* l, const uint8_t* r, int w, int 
 void cspm_pc_destroy(cspm_pc_t* pc) {
   if (!pc) return;
   cudaSetDevice(pc->device);
-  if (pc->stream) {
-    cudaStreamSynchronize(pc->stream);
-    cudaStreamDestroy(pc->stream);
-  }
+  cudaStreamSynchronize(pc->stream);
+  if (pc->own_stream) cudaStreamDestroy(pc->stream);
   pc->arena.release();
   delete pc;
 }

@@ -72,6 +72,11 @@ const char* cspm_last_error(void);
 /* Number of visible CUDA devices (0 when there is none); never fails. */
 int cspm_device_count(void);
 const char* cspm_version(void);
+/* Stream injection: handles created by the calling thread AFTER this call
+ * launch on `cuda_stream` (a cudaStream_t; e.g. the host application's or
+ * PyTorch's current stream) instead of creating a private stream; pass NULL to
+ * go back to private streams.  The stream must outlive those handles. */
+void cspm_set_thread_stream(void* cuda_stream);
 
 /* ---- CCMethod ---------------------------------------------------------- */
 /* GetCCType(name), main.cc:39-55: "GRD" -> GrdCC, "CEN" -> CenCC, else NULL. */
@@ -119,6 +124,9 @@ int cspm_pc_scale_image(const cspm_pc_t* pc, int s, int view, uint8_t* out);
 /* CSPatchMatch(l_img, r_img, max_dis, dis_scale), cs_patchmatch.cc:3-34 */
 cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis,
                           int dis_scale, uint64_t seed, int schedule, int device);
+/* Same, but l/r are DEVICE pointers on `device`. */
+cspm_pm_t* cspm_pm_create_dev(const uint8_t* d_l, const uint8_t* d_r, int w, int h, int stride,
+                              int max_dis, int dis_scale, uint64_t seed, int schedule, int device);
 void cspm_pm_destroy(cspm_pm_t* pm);
 /* PatchMatch(iter_num, plane_cost, use_pp), cs_patchmatch.cc:51-109.  pc must
  * live on the same device.  Synchronous: returns when the disparity maps are
@@ -151,6 +159,9 @@ typedef struct cspm_stats {
 } cspm_stats_t;
 int cspm_pm_stats(const cspm_pm_t* pm, cspm_stats_t* out);
 int cspm_pc_stats(const cspm_pc_t* pc, cspm_stats_t* out);
+/* In-image (border-clipped) window taps of ONE GetPlaneCost evaluation at every
+ * pixel of one view, summed over scales: the unit count behind the roofline. */
+uint64_t cspm_pc_taps_per_image_eval(const cspm_pc_t* pc);
 /* Device milliseconds spent in each CSPM_STAGE_* of the last cspm_pm_patchmatch
  * call (CUDA events on the handle's stream); ms[6]. */
 int cspm_pm_stage_ms(const cspm_pm_t* pm, float* ms);
