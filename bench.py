@@ -267,13 +267,11 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if sampler else None
 
-    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = tt.tolist()
+    from crossscalepatchmatch_b200 import shard
+
+    units, (t_dev, t_e2e) = shard.aggregate(float(w * h * d * args.steps), [t_dev, t_e2e], device=dev)
 
     if rank == 0:
-        units = w * h * d * args.steps * world
         value = units / t_dev / 1e6
         e2e = units / t_e2e / 1e6
         # roofline of the dominant kernel (k_refine, one launch per iteration, both views)

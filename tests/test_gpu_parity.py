@@ -165,3 +165,36 @@ def test_error_behaviour(cspm, pair):
     small = cspm.CSPatchMatch(l[:32, :32].copy(), r[:32, :32].copy(), D, 4)
     with pytest.raises(cspm.CspmError):
         small.PatchMatch(1, pg)                      # geometry mismatch
+
+
+def test_cpp_driver_matches_python_api(cspm, tmp_path):
+    """apps/cspm_main (the reference's main() flow over include/cspm.hpp, C++ host
+    code -> C ABI) must produce the same disparity maps as the Python mirror."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "apps", "cspm_main")
+    assert os.path.exists(exe), "apps/cspm_main not built (run __graft_entry__.build())"
+    w, h, d = 72, 50, 16
+    l, r, _ = make_pair(w, h, d, 99)
+    for name, img in (("l", l), ("r", r)):
+        with open(tmp_path / f"{name}.ppm", "wb") as f:
+            f.write(f"P6\n{w} {h}\n255\n".encode() + img[..., ::-1].tobytes())
+    out = subprocess.run([exe, f"--l_img_file={tmp_path}/l.ppm", f"--r_img_file={tmp_path}/r.ppm",
+                          f"--l_dis_file={tmp_path}/ld.pgm", f"--r_dis_file={tmp_path}/rd.pgm", "--max_dis=16",
+                          "--dis_scale=4", "--cc_name=GRD", "--use_cs", "--reg_lambda=0.3", "--use_pp", "--seed=123"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "Total Time:" in out.stdout
+    pg = cspm.PreCSPC(l, r, d, 35, 5, cspm.GetCCType("GRD"), 0.3)
+    mg = cspm.CSPatchMatch(l, r, d, 4, seed=123)
+    mg.PatchMatch(3, pg, True)
+    for v, fn in ((0, "ld.pgm"), (1, "rd.pgm")):
+        raw = open(tmp_path / fn, "rb").read()
+        img = np.frombuffer(raw[-w * h:], np.uint8).reshape(h, w)
+        assert np.array_equal(img, mg.dis(v))
+    # error behaviour: unknown cost name -> failure exit, like the reference's NULL cc
+    bad = subprocess.run([exe, f"--l_img_file={tmp_path}/l.ppm", f"--r_img_file={tmp_path}/r.ppm", "--max_dis=16",
+                          "--dis_scale=4", "--cc_name=BSM"], capture_output=True, text=True)
+    assert bad.returncode != 0
