@@ -64,6 +64,7 @@ SIGNATURES = {
     "cspm_pm_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cspm_pc_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cspm_pm_stage_ms": (C.c_int, [C.c_void_p, _fp]),
+    "cspm_debug_counters": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
 }
 
 if not os.path.exists(LIB_PATH):

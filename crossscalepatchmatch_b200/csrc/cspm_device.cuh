@@ -158,13 +158,19 @@ struct RawCtx {
   double k_grd;
   int dir;  // partner x = q_x + dir*d : -1 for the left view, +1 for the right view
 };
+// min(|x|, TAU_GRD) as the reference's `grdDiff > TAU_GRD ? TAU_GRD : grdDiff` (no NaN handling needed:
+// inputs are finite), cheaper than fmin(), which must honour NaN semantics.
+__device__ __forceinline__ double abs_min2(double x) {
+  const double ax = fabs(x);
+  return ax > 2.0 ? 2.0 : ax;
+}
 __device__ __forceinline__ double raw_grd(const RawCtx& r, int row_off, int qx, uint32_t cq, double gq, int d) {
   const int idx = row_off + qx + r.dir * d;
   const uint32_t cp = r.col_o[idx];
   const double gp = r.grd_o[idx];
   const int sad = min((int)__vsadu4(cq, cp), kLutC - 1);
-  const double clr = r.lut_c[sad];                 // ALPHA * min(sum*0.3333333333, TAU_CLR)
-  const double grd = fmin(fabs(dsub(gq, gp)), 2.0);  // min(|lG-rG|, TAU_GRD)
+  const double clr = r.lut_c[sad];               // ALPHA * min(sum*0.3333333333, TAU_CLR)
+  const double grd = abs_min2(dsub(gq, gp));     // min(|lG-rG|, TAU_GRD)
   return dadd(clr, dmul(r.k_grd, grd));
 }
 
@@ -177,10 +183,9 @@ struct TapCtx {
   double max_cost;
   int max_disp;
 };
-__device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx, uint32_t Ip, double a,
-                                           double q_disp_y) {
-  const uint32_t Iq = t.col_v[row_off + qx];
-  const double wgt = t.lut_w[__vsadu4(Ip, Iq)];
+// the plane-dependent part: wgt * (max_cost | lerp of the two raw costs)
+__device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double wgt, double a,
+                                            double q_disp_y) {
   const double q_disp = dadd(dmul(a, (double)qx), q_disp_y);
   const int fl = __double2int_rz(q_disp);  // static_cast<int>: truncation toward zero
   if (fl <= 0 || fl >= t.max_disp) return dmul(wgt, t.max_cost);
@@ -190,6 +195,12 @@ __device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx,
   const double c1 = raw_grd(t.raw, row_off, qx, Iq, gq, fl + 1);
   const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
   return dmul(wgt, tmp);
+}
+__device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx, uint32_t Ip, double a,
+                                           double q_disp_y) {
+  const uint32_t Iq = t.col_v[row_off + qx];
+  const double wgt = t.lut_w[__vsadu4(Ip, Iq)];
+  return tap_value(t, row_off, qx, Iq, wgt, a, q_disp_y);
 }
 
 __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, const double* lut_w,
@@ -211,8 +222,17 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 
 // PreSSPC::GetPlaneCost window at one scale, literal row-major accumulation
 // order (pre_ss_pc.cc:84-116 / pre_cs_pc.cc:151-181).
+//
+// Exact early termination: every addend is >= 0 and IEEE addition is monotone,
+// so the running sum never decreases.  The caller only asks "is the cost <
+// bound?" (strict, cs_patchmatch.cc:182,192,201,209,270,335); once the running
+// total — for PreCSPC: cost_prev + sum*w_s, evaluated with the same roundings
+// as the final expression — has reached `bound`, the answer is "no" whatever
+// the remaining taps add, and the (partial) value returned is still >= bound.
+// Pass bound = +inf to get the full sum.  Checked once per window row.
 __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int rx, int ry, double a, double b,
-                                              double c, const double* lut_w, const double* lut_c) {
+                                              double c, const double* lut_w, const double* lut_c, double bound,
+                                              double cost_prev, double w_s) {
   const ScaleDev& sc = pc.sc[s];
   const TapCtx t = make_tap_ctx(pc, s, v, lut_w, lut_c);
   const int hw = pc.half_wnd;
@@ -224,23 +244,27 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
     const double q_disp_y = dadd(dmul(b, (double)qy), c);
     const int row_off = qy * sc.pitch + sc.pad;
     for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term(t, row_off, qx, Ip, a, q_disp_y));
+    const double total = pc.cross_scale ? dadd(cost_prev, dmul(cost, w_s)) : cost;
+    if (total >= bound) break;
   }
   return cost;
 }
 
 // IPlaneCost::GetPlaneCost: PreSSPC (pre_ss_pc.cc:74-118) or PreCSPC
-// (pre_cs_pc.cc:133-188).
+// (pre_cs_pc.cc:133-188).  Returns the exact cost if it is < bound, otherwise
+// some value >= bound (see window_cost).
 __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int ry, const PlaneD& p,
-                                             const double* lut_w, const double* lut_c) {
-  if (!pc.cross_scale) return window_cost(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c);
+                                             const double* lut_w, const double* lut_c, double bound) {
+  if (!pc.cross_scale) return window_cost(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);
   int cx = rx, cy = ry;
   for (int s = 0; s < pc.scale_num; ++s) {
     PlaneD q = p;
     update_param(q, (double)cx, (double)cy, cur_disp);
-    const double sc_cost = window_cost(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c);
+    const double sc_cost = window_cost(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
     cost = dadd(cost, dmul(sc_cost, pc.scale_wgt[s]));
+    if (cost >= bound) break;
     cy /= 2;
     cx /= 2;
     cur_disp = ddiv(cur_disp, 2.0);
@@ -253,6 +277,199 @@ __device__ __forceinline__ void stage_luts(const PcDev& pc, double* s_lut_w, dou
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < kLutW; i += blockDim.x * blockDim.y) s_lut_w[i] = pc.lut_w[i];
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < kLutC; i += blockDim.x * blockDim.y) s_lut_c[i] = pc.lut_c[i];
   __syncthreads();
+}
+
+// ===========================================================================
+// Streaming evaluator ("engine"): GetPlaneCost for up to 32 planes at once with
+// the lanes of the PRODUCER warps laid along consecutive window taps (so the
+// guide row, the gradient row and the partner row segment of one plane are read
+// coalesced whatever the plane is), and ONE CONSUMER warp — the last warp of
+// the CTA, i.e. the highest scheduling priority on its sub-partition — whose
+// lane L adds the addends of chain L in the reference's row-major order
+// (pre_ss_pc.cc:84-116).  Producers fill chunk i+1 (whole window rows) of a
+// double-buffered shared-memory array while the consumer drains chunk i, so 32
+// serial f64 add chains run side by side, overlapped with addend production.
+// The sums are therefore rounded exactly like the reference's scalar loop.
+//
+//   WND   window size if known at compile time (35 in the reference), 0 = runtime
+//   ROWS  window rows per chunk for WND = 35 (buffer holds ROWS*35 addends per chain)
+//   NT    threads per CTA (NT/32 - 1 producer warps + 1 consumer warp)
+//   PAIRS chains 2p and 2p+1 share centre pixel and view (the two candidates of
+//         one pixel in spatial propagation): the adaptive weight is computed once
+// ===========================================================================
+struct ChainDesc {  // per-scale description of one chain, written by its consumer lane
+  double a, b, c;
+  int v, cx, cy, on;
+  uint32_t Ip;
+  int pad_;
+};
+
+template <int ROWS>
+struct EngineCfg {
+  static constexpr int kChunkMax = ROWS * 35;
+  static constexpr int kStride = kChunkMax + 1 + (kChunkMax & 1);  // odd number of doubles: conflict-free chain reads
+  static constexpr size_t kTermsDoubles = 2 * 32 * (size_t)kStride;
+  static constexpr size_t kSmemBytes = sizeof(double) * (kLutW + kLutC + kTermsDoubles) + 32 * sizeof(ChainDesc);
+};
+
+struct EngineSmem {
+  double* lut_w;
+  double* lut_c;
+  double* terms;
+  ChainDesc* ch;
+};
+template <int ROWS>
+__device__ __forceinline__ EngineSmem engine_smem(double* dyn) {
+  EngineSmem e;
+  e.lut_w = dyn;
+  e.lut_c = e.lut_w + kLutW;
+  e.terms = e.lut_c + kLutC;
+  e.ch = reinterpret_cast<ChainDesc*>(e.terms + EngineCfg<ROWS>::kTermsDoubles);
+  return e;
+}
+
+// Every thread of the CTA calls this with CTA-uniform control flow.  Consumer
+// lanes pass their chain (ch_on, view, reference pixel, plane, bound); the
+// aggregated cost comes back in the consumer lanes (other threads get 0).
+//
+// Chains come in PAIRS (2p, 2p+1) that share centre pixel and view — the two
+// candidates of one pixel in spatial propagation — so the adaptive weight of a
+// tap is computed once per pair.  A production item is (pair, tap); items are
+// spread evenly over all producer threads, lanes along consecutive taps.
+//
+// Exact early termination (see window_cost): after each chunk the consumer
+// lane compares its running total with `bound`; once reached, the chain is
+// switched off (its remaining addends are neither produced nor added) and the
+// partial total (>= bound) is returned.
+__device__ unsigned long long g_eng_prof[4];  // diagnostic: {consumer busy, producer warp 0 busy, chunk loop total, -} of CTA gridDim/2
+struct PairDesc {  // 64 B, written by the consumer lanes, read (broadcast) by the producers
+  double a0, b0, c0, a1, b1, c1;
+  int cx, cy;
+  uint32_t Ip;
+  int flags;  // bit0: view, bit1: chain 2p on, bit2: chain 2p+1 on
+};
+
+template <int WND, int ROWS, int NT>
+__device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const EngineSmem& sm, int nch, bool ch_on, int ch_v,
+                                                    int ch_x, int ch_y, const PlaneD& ch_plane, double ch_bound) {
+  constexpr int kStride = EngineCfg<ROWS>::kStride;
+  constexpr int kProducers = NT - 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool consumer = warp == NT / 32 - 1;
+  const int wnd = WND > 0 ? WND : 2 * pc.half_wnd + 1;
+  const int chunk_rows = WND > 0 ? ROWS : max(1, EngineCfg<ROWS>::kChunkMax / wnd);
+  const int nchunks = (wnd + chunk_rows - 1) / chunk_rows;
+  const int npairs = (nch + 1) >> 1;
+  PairDesc* pd = reinterpret_cast<PairDesc*>(sm.ch);  // 16 x 64 B <= 32 x sizeof(ChainDesc)
+  double cost = 0.0, disp = 0.0, sum = 0.0;
+  int cx = ch_x, cy = ch_y;
+  bool live = ch_on;
+  if (consumer && ch_on && pc.cross_scale) disp = plane_disp(ch_plane, ch_x, ch_y);
+  for (int s = 0; s < pc.scale_num; ++s) {
+    const ScaleDev& sc = pc.sc[s];
+    if (consumer) {
+      PlaneD q = ch_plane;
+      if (live && pc.cross_scale) update_param(q, (double)cx, (double)cy, disp);  // pre_cs_pc.cc:144
+      const int on_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
+      if (lane < 2 * npairs) {
+        PairDesc& d = pd[lane >> 1];
+        if (lane & 1) {
+          d.a1 = q.a; d.b1 = q.b; d.c1 = q.c;
+        } else {
+          d.a0 = q.a; d.b0 = q.b; d.c0 = q.c;
+          d.cx = cx; d.cy = cy;
+          d.Ip = sc.color[ch_v][cy * sc.pitch + sc.pad + cx];
+          d.flags = ch_v | (live ? 2 : 0) | (on_other ? 4 : 0);
+        }
+      }
+      sum = 0.0;
+    }
+    __syncthreads();
+    // image pointers of this scale for both views (uniform), selected per item by the pair's view
+    const uint32_t* col0 = sc.color[0];
+    const uint32_t* col1 = sc.color[1];
+    const double* grd0 = sc.grad[0];
+    const double* grd1 = sc.grad[1];
+    const bool prof = blockIdx.x == gridDim.x / 2 && lane == 0;
+    const long long loop_t0 = clock64();
+    for (int ci = 0; ci <= nchunks; ++ci) {
+      const long long it_t0 = clock64();
+      if (!consumer) {
+        if (ci < nchunks) {  // produce chunk ci (whole window rows)
+          const int dy0 = ci * chunk_rows, len = min(chunk_rows, wnd - dy0) * wnd;
+          double* buf = sm.terms + (size_t)(ci & 1) * 32 * kStride;
+          const unsigned int magic = 0xFFFFFFFFu / (unsigned int)len + 1u;  // it / len for it < 2^16
+          const int nitems = npairs * len;
+          for (int it = threadIdx.x; it < nitems; it += kProducers) {
+            const int gi = (int)__umulhi((unsigned int)it, magic), kk = it - gi * len;
+            const PairDesc& d = pd[gi];
+            const int flags = d.flags;
+            if (!(flags & 6)) continue;
+            const int dy = kk / wnd, dx = kk - dy * wnd;
+            const int qy = d.cy + dy0 + dy - pc.half_wnd, qx = d.cx + dx - pc.half_wnd;
+            double t0 = 0.0, t1 = 0.0;  // +0.0: additive identity of these non-negative sums
+            if (qy >= 0 && qy < sc.h && qx >= 0 && qx < sc.w) {
+              const int v = flags & 1;
+              TapCtx tc;
+              tc.col_v = v ? col1 : col0;
+              tc.grd_v = v ? grd1 : grd0;
+              tc.lut_w = sm.lut_w;
+              tc.raw.col_o = v ? col0 : col1;
+              tc.raw.grd_o = v ? grd0 : grd1;
+              tc.raw.lut_c = sm.lut_c;
+              tc.raw.k_grd = pc.k_grd;
+              tc.raw.dir = v ? 1 : -1;
+              tc.max_cost = sc.max_cost[v];
+              tc.max_disp = sc.max_disp;
+              const int row_off = qy * sc.pitch + sc.pad;
+              const uint32_t Iq = tc.col_v[row_off + qx];
+              const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
+              const double qyd = (double)qy;
+              if (flags & 2) t0 = tap_value(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+              if (flags & 4) t1 = tap_value(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+            }
+            buf[(2 * gi) * kStride + kk] = t0;
+            buf[(2 * gi + 1) * kStride + kk] = t1;
+          }
+        }
+      } else {
+        if (ci > 0 && live) {  // consume chunk ci-1 in tap order
+          const int dy0 = (ci - 1) * chunk_rows, rows = min(chunk_rows, wnd - dy0);
+          const double* tp = sm.terms + (size_t)((ci - 1) & 1) * 32 * kStride + lane * kStride;
+          if (WND > 0) {
+            for (int r = 0; r < rows; ++r) {
+#pragma unroll
+              for (int kk = 0; kk < (WND > 0 ? WND : 1); ++kk) sum = dadd(sum, tp[r * (WND > 0 ? WND : 1) + kk]);
+            }
+          } else {
+            const int len = rows * wnd;
+#pragma unroll 8
+            for (int kk = 0; kk < len; ++kk) sum = dadd(sum, tp[kk]);
+          }
+          const double total = pc.cross_scale ? dadd(cost, dmul(sum, pc.scale_wgt[s])) : sum;
+          if (total >= ch_bound) live = false;  // rejected for certain: stop this chain
+        }
+        // publish switched-off chains so producers skip them from the next chunk on
+        const int live_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
+        if (ci > 0 && lane < 2 * npairs && !(lane & 1)) {
+          const int f = ch_v | (live ? 2 : 0) | (live_other ? 4 : 0);
+          if (f != pd[lane >> 1].flags) pd[lane >> 1].flags = f;
+        }
+      }
+      if (prof && consumer) g_eng_prof[0] += (unsigned long long)(clock64() - it_t0);
+      if (prof && warp == 0) g_eng_prof[1] += (unsigned long long)(clock64() - it_t0);
+      __syncthreads();
+    }
+    if (prof && warp == 0) g_eng_prof[2] += (unsigned long long)(clock64() - loop_t0);
+    if (consumer && ch_on) {
+      if (pc.cross_scale) cost = dadd(cost, dmul(sum, pc.scale_wgt[s]));  // pre_cs_pc.cc:182
+      else cost = sum;
+      disp = ddiv(disp, 2.0);
+    }
+    cx /= 2;
+    cy /= 2;
+  }
+  return cost;
 }
 
 }  // namespace cspm

@@ -119,6 +119,7 @@ struct cspm_pm {
   unsigned long long* tmin = nullptr;
   unsigned int* win = nullptr;
   unsigned long long* tap_counter = nullptr;
+  unsigned int* grid_barrier = nullptr;  // persistent spatial sweep
   // post-processing scratch
   int* valid[2] = {nullptr, nullptr};
   uint8_t* dis_tmp = nullptr;

@@ -14,7 +14,11 @@
 // DESIGN.md "Schedules"), so planes, costs and disparities are bit-identical
 // to the reference code run with the same RNG streams.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+
+#include <math_constants.h>
 
 #include "cspm_internal.h"
 
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
   PlaneD p;
   p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
   update_param(p, (double)x, (double)y, z);
-  const double cost = plane_cost(pc, v, x, y, p, s_lut_w, s_lut_c);
+  const double cost = plane_cost(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
   store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
 }
 
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
     const double inv = ddiv(1.0, denom);
     q.nx = dmul(q.nx, inv); q.ny = dmul(q.ny, inv); q.nz = dmul(q.nz, inv);
     update_param(q, (double)x, (double)y, z);
-    const double cost = plane_cost(pc, v, x, y, q, s_lut_w, s_lut_c);
+    const double cost = plane_cost(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
     if (cost < cur_cost) {
       cur = q;
       cur_cost = cost;
@@ -215,7 +219,9 @@ __global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, do
     PlaneD q;
     int cor_x;
     view_candidate(pm, v, x, y, &q, &cor_x);
-    const double cost = plane_cost(pc, v, cor_x, y, q, s_lut_w, s_lut_c);
+    // a proposal can only win if it beats the target's cost at the start of this pass
+    const double bound = pm.st[v][6 * (size_t)pm.w * pm.h + (size_t)y * pm.w + cor_x];
+    const double cost = plane_cost(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;
     cand_tx[i] = cor_x;
@@ -255,6 +261,8 @@ __global__ void k_view_commit(PmDev pm, int v, int rev, const double* cand_cost,
   view_candidate(pm, v, x, y, &q, &cor_x);
   store_plane(pm.st[v], n, t, q, cand_cost[i]);
 }
+
+#include "cspm_pm_engine.cuh"
 
 // -------------------------------------------------------------- plane2disp
 __global__ void k_plane2disp(PmDev pm, uint8_t* dis0, uint8_t* dis1) {
@@ -405,13 +413,39 @@ static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
 static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const int rev = (iter % 2 == 0) ? 0 : 1;
   const int wnd = 2 * pc->dev.half_wnd + 1;
-  const size_t smem = sizeof(double) * (kLutW + kLutC + 2 * (size_t)wnd * wnd);
-  const PmDev d = pm_dev(pm);
-  for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
-    const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
-    dim3 g(u_hi - u_lo + 1, 2);
-    k_spatial_diag<<<g, 128, smem, pm->stream>>>(pc->dev, d, diag, u_lo, rev);
+  PmDev d = pm_dev(pm);
+  PcDev pcd = pc->dev;
+  static const bool force_diag = [] {
+    const char* e = getenv("CSPM_SPATIAL");
+    return e && std::string(e) == "diag";
+  }();
+  bool persistent = !force_diag;
+  const size_t smem_p = EngineCfg<kSpRows>::kSmemBytes;
+  int sms = 0, coop = 0, occ = 0;
+  auto kern = wnd == 35 ? k_spatial_persist<35> : k_spatial_persist<0>;
+  if (persistent) {
+    CSPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pm->device));
+    CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm->device));
+    CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSpThreads, smem_p));
+    persistent = coop && occ >= kSpCtasPerSm;
+  }
+  if (persistent) {
+    // one cooperative launch per sweep; the grid barrier needs every CTA resident
+    CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int), pm->stream));
+    int rev_arg = rev;
+    unsigned int* bar = pm->grid_barrier;
+    void* args[] = {&pcd, &d, &rev_arg, &bar};
+    CSPM_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(sms * kSpCtasPerSm), dim3(kSpThreads), args, smem_p, pm->stream));
     pm->stats.kernel_launches++;
+  } else {
+    const size_t smem = sizeof(double) * (kLutW + kLutC + 2 * (size_t)wnd * wnd);
+    for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
+      const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
+      dim3 g(u_hi - u_lo + 1, 2);
+      k_spatial_diag<<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
+      pm->stats.kernel_launches++;
+    }
   }
   // evaluations: every pixel with an x-neighbour + every pixel with a y-neighbour, both views
   const uint64_t ev = 2ull * ((uint64_t)(pm->w - 1) * pm->h + (uint64_t)pm->w * (pm->h - 1));
@@ -509,6 +543,7 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
       pm->win = pm->arena.alloc<unsigned int>(n);
       pm->dis_tmp = pm->arena.alloc<uint8_t>(n);
       pm->tap_counter = pm->arena.alloc<unsigned long long>(1);
+      pm->grid_barrier = pm->arena.alloc<unsigned int>(1);
       CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(unsigned long long), pm->stream));
       CSPM_CUDA(cudaStreamSynchronize(pm->stream));
       return pm;
@@ -654,6 +689,20 @@ int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const doub
     }
     CSPM_CUDA(cudaMemcpyAsync(pm->st[view], h.data(), sizeof(double) * 7 * n, cudaMemcpyHostToDevice, pm->stream));
     CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  });
+}
+
+int cspm_debug_counters(unsigned long long* out8, int reset) {
+  return guard([&] {
+    CSPM_REQUIRE(out8, "null argument");
+    CSPM_CUDA(cudaDeviceSynchronize());
+    CSPM_CUDA(cudaMemcpyFromSymbol(out8, g_sp_prof, sizeof(unsigned long long) * 4));
+    CSPM_CUDA(cudaMemcpyFromSymbol(out8 + 4, g_eng_prof, sizeof(unsigned long long) * 4));
+    if (reset) {
+      unsigned long long z[8] = {};
+      CSPM_CUDA(cudaMemcpyToSymbol(g_sp_prof, z, sizeof z));
+      CSPM_CUDA(cudaMemcpyToSymbol(g_eng_prof, z, sizeof(unsigned long long) * 4));
+    }
   });
 }
 

@@ -1,0 +1,119 @@
+// cspm_pm_engine.cuh — PatchMatch stages on the streaming evaluator
+// (cspm_device.cuh: engine_eval).  Included by cspm_pm.cu inside namespace cspm.
+//
+//   k_spatial_persist   SpatialPropagation: one cooperative launch per sweep,
+//                       grid barrier between anti-diagonals, 16 pixels x 2
+//                       candidates per CTA per pass
+// (The bulk stages — init, refinement, view propagation — stay thread-per-pixel:
+// an engine version of them was measured 1.8x slower, 950 vs 535 ms per HD run,
+// because every pixel has only one live candidate at a time.)
+#pragma once
+
+constexpr int kSpThreads = 1024;
+constexpr int kSpCtasPerSm = 1;
+constexpr int kSpTasks = 16;  // pixels per CTA per pass: one producer warp per pixel at least
+constexpr int kSpRows = 5;      // window rows per pipeline chunk (WND = 35)
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Cycle accounting of the persistent sweep (CTA 0 only; read back through
+// cspm_debug_counters): {task setup, evaluation, accept, grid barrier}.
+__device__ unsigned long long g_sp_prof[8];
+#define SP_PROF(slot)                                              \
+  do {                                                             \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                     \
+      const long long now__ = clock64();                           \
+      g_sp_prof[slot] += (unsigned long long)(now__ - prof_t);     \
+      prof_t = now__;                                              \
+    }                                                              \
+  } while (0)
+
+template <int WND>
+__global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(PcDev pc, PmDev pm, int rev, unsigned int* barrier_ctr) {
+  extern __shared__ double s_dyn[];
+  const EngineSmem sm = engine_smem<kSpRows>(s_dyn);
+  stage_luts(pc, sm.lut_w, sm.lut_c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool consumer = warp == kSpThreads / 32 - 1;
+  const size_t n = (size_t)pm.w * pm.h;
+  const int inc = rev ? -1 : 1;
+  unsigned int bar_target = 0;
+  long long prof_t = clock64();
+
+  for (int diag = 1; diag <= pm.w + pm.h - 2; ++diag) {
+    const int u_lo = max(0, diag - (pm.h - 1)), u_hi = min(diag, pm.w - 1);
+    // Balanced CONTIGUOUS partition of the diagonal's pixels over the CTAs: neighbouring pixels share
+    // 94 % of their windows and a CTA's range barely moves from one diagonal to the next, so the
+    // window data stays in this SM's L1 (a round-robin assignment re-fetched everything from L2).
+    const int npix = u_hi - u_lo + 1;
+    const int pq = npix / (int)gridDim.x, pr = npix % (int)gridDim.x;
+    const int pix0 = (int)blockIdx.x * pq + min((int)blockIdx.x, pr);
+    const int ntasks_mine = 2 * (pq + ((int)blockIdx.x < pr ? 1 : 0));  // task = pixel of one view
+    for (int base = 0; base < ntasks_mine; base += kSpTasks) {
+      const int nt = min(kSpTasks, ntasks_mine - base);
+      // consumer lane L <-> (task L>>1, candidate L&1): x-axis neighbour, y-axis neighbour
+      PlaneD ch_plane = {};
+      double ch_min = 0.0;
+      size_t ch_idx = 0;
+      bool ch_on = false;
+      int ch_v = 0, ch_x = 0, ch_y = 0;
+      const int ti_c = lane >> 1, cc = lane & 1;
+      if (consumer && ti_c < nt) {
+        const int tid = 2 * pix0 + base + ti_c;
+        const int u = u_lo + (tid >> 1), t = diag - u;
+        ch_v = tid & 1;
+        ch_x = rev ? pm.w - 1 - u : u;
+        ch_y = rev ? pm.h - 1 - t : t;
+        ch_idx = (size_t)ch_y * pm.w + ch_x;
+        ch_on = cc == 0 ? u >= 1 : t >= 1;
+        const double* st = pm.st[ch_v];
+        if (ch_on) {
+          // neighbour planes were written by another SM on the previous diagonal: bypass L1
+          const size_t j = cc == 0 ? ch_idx - inc : ch_idx - (ptrdiff_t)inc * pm.w;
+          ch_plane.nx = __ldcg(st + j); ch_plane.ny = __ldcg(st + n + j); ch_plane.nz = __ldcg(st + 2 * n + j);
+          ch_plane.a = __ldcg(st + 3 * n + j); ch_plane.b = __ldcg(st + 4 * n + j); ch_plane.c = __ldcg(st + 5 * n + j);
+        }
+        if (cc == 0) ch_min = __ldcg(st + 6 * n + ch_idx);
+      }
+      // both candidates must beat the pixel's cost at the start of the step (cs_patchmatch.cc:201,209)
+      const double ch_bound = __shfl_sync(0xffffffffu, ch_min, lane & ~1);
+      SP_PROF(0);
+      const double ch_cost = engine_eval_pairs<WND, kSpRows, kSpThreads>(pc, sm, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound);
+      SP_PROF(1);
+      // acceptance in the reference's order: x-axis neighbour, then y-axis neighbour (:198-212)
+      if (consumer) {
+        const double c1 = __shfl_down_sync(0xffffffffu, ch_cost, 1);
+        const bool on1 = __shfl_down_sync(0xffffffffu, (int)ch_on, 1) != 0;
+        int best = -1;
+        double min_cost = ch_min;
+        if (cc == 0 && ti_c < nt) {
+          if (ch_on && ch_cost < min_cost) { min_cost = ch_cost; best = 0; }
+          if (on1 && c1 < min_cost) { min_cost = c1; best = 1; }
+        }
+        const int best_up = __shfl_up_sync(0xffffffffu, best, 1);
+        const int my_best = cc == 0 ? best : best_up;
+        if (ti_c < nt && my_best == cc) {  // the lane that owns the winning candidate writes it
+          store_plane(pm.st[ch_v], n, ch_idx, ch_plane, ch_cost);
+          __threadfence();
+        }
+      }
+      SP_PROF(2);
+    }
+    bar_target += gridDim.x;
+    grid_barrier(barrier_ctr, bar_target);
+    SP_PROF(3);
+  }
+}
+

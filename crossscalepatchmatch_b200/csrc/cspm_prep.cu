@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <math_constants.h>
+
 #include "cspm_internal.h"
 
 namespace cspm {
@@ -134,7 +136,7 @@ __global__ void k_plane_cost_batch(PcDev pc, int n, const int* __restrict__ x, c
   PlaneD p;
   p.nx = normal[3 * i]; p.ny = normal[3 * i + 1]; p.nz = normal[3 * i + 2];
   update_param(p, point[3 * i], point[3 * i + 1], point[3 * i + 2]);
-  out[i] = plane_cost(pc, view[i], x[i], y[i], p, s_lut_w, s_lut_c);
+  out[i] = plane_cost(pc, view[i], x[i], y[i], p, s_lut_w, s_lut_c, CUDART_INF);
 }
 
 // buildCV / buildRightCV export for arbitrary CV_64FC3 input (cc/grd_cc.cpp:60-154).

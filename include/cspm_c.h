@@ -165,6 +165,10 @@ uint64_t cspm_pc_taps_per_image_eval(const cspm_pc_t* pc);
 /* Device milliseconds spent in each CSPM_STAGE_* of the last cspm_pm_patchmatch
  * call (CUDA events on the handle's stream); ms[6]. */
 int cspm_pm_stage_ms(const cspm_pm_t* pm, float* ms);
+/* Diagnostic: SM-cycle totals spent by CTA 0 of the persistent spatial sweep in
+ * {task setup, per-scale prep, chunk pipeline, accept, grid barrier, -, -, -}
+ * on the current device since the last reset; out8[8]. */
+int cspm_debug_counters(unsigned long long* out8, int reset);
 
 #ifdef __cplusplus
 }
