@@ -46,7 +46,7 @@ W_HD, H_HD, D_HD = 1920, 1080, 256
 ITERS = 3
 WND = 35
 BYTES_PER_TAP = 19  # 3 B guide pixel + 2 x 8 B cost samples (pre_ss_pc.cc:93,109-110)
-CPU_CROP = (240, 136)  # bounded CPU sample (w, h), same max_dis
+CPU_CROP = (384, 216)  # bounded CPU sample (w, h), same max_dis: ~10-30 s of CPU work per pass
 
 
 def parse():
@@ -109,7 +109,7 @@ def run_reference(args):
     from crossscalepatchmatch_b200.synth import SEED_BASE
 
     l, r, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     kind = "port"
     for _ in range(min(args.warmup, 1)):  # one CPU warm-up pass is plenty (no JIT, no caches to prime)
         cpu_run(l, r, d, args.use_cs, cores)
@@ -254,6 +254,8 @@ def run_b200(args):
         refine_ms.append(last["stage_ms"][c.STAGE_REFINE] / ITERS)
     barrier()
     t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    if os.environ.get("CSPM_BENCH_DEBUG"):
+        print(f"[rank {rank}] per-step device ms: {[round(a.elapsed_time(b), 1) for a, b in ev]} stage_ms {last['stage_ms']}", file=sys.stderr, flush=True)
     gpu_launches = launches["n"]
 
     # end-to-end leg: host buffers in, disparity maps out
@@ -307,7 +309,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cl, cr, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
-            cores = os.cpu_count() or 1
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             t, kind = cpu_run(cl, cr, d, args.use_cs, cores)
             line["cpu_baseline"] = {"value": cw * ch * d / t / 1e6, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind,
                                     "sample": f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline, 1 pass ({t:.1f} s)"}

@@ -65,17 +65,22 @@ void use_device(int device);
 // or a fresh private one.  *owned tells the destructor whether to destroy it.
 cudaStream_t acquire_stream(bool* owned);
 
+// Stream-ordered allocations from the device's default memory pool.  The pool
+// keeps freed blocks (release threshold = unlimited, set in use_device), so the
+// create / destroy churn of per-pair handles costs no cudaMalloc / cudaFree
+// after the first pair.
 struct DeviceArena {
   std::vector<void*> ptrs;
+  cudaStream_t stream = nullptr;
   template <typename T>
   T* alloc(size_t n) {
     void* p = nullptr;
-    CSPM_CUDA(cudaMalloc(&p, n * sizeof(T) + 256));  // slack: vector loads may touch the tail
+    CSPM_CUDA(cudaMallocAsync(&p, n * sizeof(T) + 256, stream));  // slack: vector loads may touch the tail
     ptrs.push_back(p);
     return (T*)p;
   }
   void release() {
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
     ptrs.clear();
   }
 };

@@ -523,6 +523,7 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
       for (double z = max_dis / 2.0; z >= 0.1; z /= 2.0) ++nr;  // kZStopThres_ = 0.1
       pm->n_ref = nr;
       pm->stream = acquire_stream(&pm->own_stream);
+      pm->arena.stream = pm->stream;
       const size_t n = (size_t)w * h;
       for (int v = 0; v < 2; ++v) {
         pm->st[v] = pm->arena.alloc<double>(7 * n);
@@ -567,9 +568,9 @@ cspm_pm_t* cspm_pm_create_dev(const uint8_t* l, const uint8_t* r, int w, int h, 
 void cspm_pm_destroy(cspm_pm_t* pm) {
   if (!pm) return;
   cudaSetDevice(pm->device);
+  pm->arena.release();
   cudaStreamSynchronize(pm->stream);
   if (pm->own_stream) cudaStreamDestroy(pm->stream);
-  pm->arena.release();
   delete pm;
 }
 

@@ -38,6 +38,14 @@ void use_device(int device) {
                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (device < 0 || device >= n) throw Error(CSPM_EINVAL, "device index out of range");
   CSPM_CUDA(cudaSetDevice(device));
+  static bool pool_set[64] = {};
+  if (device < 64 && !pool_set[device]) {  // keep freed blocks in the pool (see DeviceArena)
+    cudaMemPool_t pool;
+    CSPM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CSPM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_set[device] = true;
+  }
 }
 
 // ------------------------------------------------------------------ kernels
@@ -266,6 +274,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     pc->wnd_size = wnd_size;
     pc->scale_num = cross_scale ? scale_num : 1;
     pc->stream = acquire_stream(&pc->own_stream);
+    pc->arena.stream = pc->stream;
     cudaStream_t st = pc->stream;
     PcDev& D = pc->dev;
     D.cc_kind = cc->kind;
@@ -444,6 +453,7 @@ int cspm_cc_build_cv(const cspm_cc_t* cc, const double* l_rgb, const double* r_r
       k_build_cv_grd<<<gv, 128>>>(d_l, d_r, d_lg, d_rg, w, h, max_dis, right_view, d_vol);
       CSPM_CUDA(cudaGetLastError());
       CSPM_CUDA(cudaMemcpy(cost_vol, d_vol, sizeof(double) * n * max_dis, cudaMemcpyDeviceToHost));
+      CSPM_CUDA(cudaDeviceSynchronize());
     } catch (...) {
       A.release();
       throw;
@@ -471,9 +481,9 @@ cspm_pc_t* cspm_pc_create_cs_dev(const uint8_t* l, const uint8_t* r, int w, int 
 void cspm_pc_destroy(cspm_pc_t* pc) {
   if (!pc) return;
   cudaSetDevice(pc->device);
+  pc->arena.release();
   cudaStreamSynchronize(pc->stream);
   if (pc->own_stream) cudaStreamDestroy(pc->stream);
-  pc->arena.release();
   delete pc;
 }
 
@@ -489,6 +499,7 @@ int cspm_pc_get_plane_cost(const cspm_pc_t* pc, int n, const int* x, const int* 
     }
     use_device(pc->device);
     DeviceArena A;
+    A.stream = pc->stream;
     try {
       int* d_x = A.alloc<int>(n);
       int* d_y = A.alloc<int>(n);
