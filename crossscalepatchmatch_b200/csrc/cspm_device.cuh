@@ -472,4 +472,182 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
   return cost;
 }
 
+// ---------------------------------------------------------------------------
+// Ring-buffer form of engine_eval_pairs for the reference's 35x35 window: no
+// CTA-wide barrier inside an evaluation.  Producers stream through ALL window
+// rows of all pairs (items ordered row-major, so rows complete in order) and
+// publish per-row completion counts in shared memory; the consumer warp waits
+// for row r, adds its 35 addends per chain in tap order, and publishes its
+// progress so producers never overwrite a row that is still unread (ring of
+// kRing rows).  This removes the per-chunk barriers and the load-quantisation
+// loss of the chunked pipeline (1.3 items per thread per chunk -> 2 rounds).
+// ---------------------------------------------------------------------------
+constexpr int kRing = 12;            // window rows in flight
+constexpr int kRingChain = 37;       // doubles per (row, chain): 35 addends, odd stride -> conflict-free reads
+constexpr int kRingRowDoubles = 32 * kRingChain;
+struct ViewCtx {     // everything a producer needs about (scale, view), copied out of the kernel parameters once
+  const uint32_t* col_v;  // per scale so that items read it with fixed-offset shared loads instead of
+  const double* grd_v;    // dynamically indexed constant-bank loads
+  const uint32_t* col_o;
+  const double* grd_o;
+  double max_cost;
+  int dir, pad_;
+};
+struct RingCtl {
+  ViewCtx view[2];
+  int w, h, pitch, pad, max_disp, pad_[3];
+  int done[36];      // addends produced per window row (items, not chains)
+  int consumed;      // rows fully read by the consumer
+  int pad2_[3];
+};
+constexpr size_t kRingSmemBytes = sizeof(double) * (kLutW + kLutC + (size_t)kRing * kRingRowDoubles) + 16 * sizeof(PairDesc) + sizeof(RingCtl);
+
+struct RingSmem {
+  double* lut_w;
+  double* lut_c;
+  double* ring;
+  PairDesc* pd;
+  RingCtl* ctl;
+};
+__device__ __forceinline__ RingSmem ring_smem(double* dyn) {
+  RingSmem e;
+  e.lut_w = dyn;
+  e.lut_c = e.lut_w + kLutW;
+  e.ring = e.lut_c + kLutC;
+  e.pd = reinterpret_cast<PairDesc*>(e.ring + (size_t)kRing * kRingRowDoubles);
+  e.ctl = reinterpret_cast<RingCtl*>(e.pd + 16);
+  return e;
+}
+
+template <int NT>
+__device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const RingSmem& sm, int nch, bool ch_on, int ch_v,
+                                                         int ch_x, int ch_y, const PlaneD& ch_plane, double ch_bound) {
+  constexpr int WND = 35, HW = 17;
+  constexpr int kProducers = NT - 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool consumer = warp == NT / 32 - 1;
+  const int npairs = (nch + 1) >> 1;
+  const int row_items = npairs * WND;
+  volatile int* v_done = sm.ctl->done;
+  volatile int* v_consumed = &sm.ctl->consumed;
+  double cost = 0.0, disp = 0.0, sum = 0.0;
+  int cx = ch_x, cy = ch_y;
+  bool live = ch_on;
+  if (consumer && ch_on && pc.cross_scale) disp = plane_disp(ch_plane, ch_x, ch_y);
+  for (int s = 0; s < pc.scale_num; ++s) {
+    const ScaleDev& sc = pc.sc[s];
+    if (consumer) {
+      PlaneD q = ch_plane;
+      if (live && pc.cross_scale) update_param(q, (double)cx, (double)cy, disp);  // pre_cs_pc.cc:144
+      const int on_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
+      if (lane < 2 * npairs) {
+        PairDesc& d = sm.pd[lane >> 1];
+        if (lane & 1) {
+          d.a1 = q.a; d.b1 = q.b; d.c1 = q.c;
+        } else {
+          d.a0 = q.a; d.b0 = q.b; d.c0 = q.c;
+          d.cx = cx; d.cy = cy;
+          d.Ip = sc.color[ch_v][cy * sc.pitch + sc.pad + cx];
+          d.flags = ch_v | (live ? 2 : 0) | (on_other ? 4 : 0);
+        }
+      }
+      for (int r = lane; r < 36; r += 32) sm.ctl->done[r] = 0;
+      if (lane == 0) sm.ctl->consumed = 0;
+      if (lane < 2) {
+        ViewCtx& vc = sm.ctl->view[lane];
+        vc.col_v = sc.color[lane]; vc.grd_v = sc.grad[lane];
+        vc.col_o = sc.color[1 - lane]; vc.grd_o = sc.grad[1 - lane];
+        vc.max_cost = sc.max_cost[lane];
+        vc.dir = lane ? 1 : -1;
+      }
+      if (lane == 2) {
+        sm.ctl->w = sc.w; sm.ctl->h = sc.h; sm.ctl->pitch = sc.pitch; sm.ctl->pad = sc.pad; sm.ctl->max_disp = sc.max_disp;
+      }
+      sum = 0.0;
+    }
+    __syncthreads();
+    if (!consumer) {
+      const int sw = sm.ctl->w, sh = sm.ctl->h, spitch = sm.ctl->pitch, spad = sm.ctl->pad, smaxd = sm.ctl->max_disp;
+      const double k_grd = pc.k_grd;
+      const unsigned int magic_row = 0xFFFFFFFFu / (unsigned int)row_items + 1u;
+      const int total = WND * row_items;
+      for (int it = threadIdx.x; it < total; it += kProducers) {
+        const int r = (int)__umulhi((unsigned int)it, magic_row);
+        const int rem = it - r * row_items;
+        const int gi = rem / WND, dx = rem - gi * WND;
+        if (r >= kRing) {  // ring slot still unread?
+          while (*v_consumed <= r - kRing) __nanosleep(40);
+        }
+        const PairDesc& d = sm.pd[gi];
+        const int flags = *reinterpret_cast<const volatile int*>(&d.flags);
+        double t0 = 0.0, t1 = 0.0;  // +0.0: additive identity of these non-negative sums
+        if (flags & 6) {
+          const int qy = d.cy + r - HW, qx = d.cx + dx - HW;
+          if (qy >= 0 && qy < sh && qx >= 0 && qx < sw) {
+            const ViewCtx& vc = sm.ctl->view[flags & 1];
+            TapCtx tc;
+            tc.col_v = vc.col_v;
+            tc.grd_v = vc.grd_v;
+            tc.lut_w = sm.lut_w;
+            tc.raw.col_o = vc.col_o;
+            tc.raw.grd_o = vc.grd_o;
+            tc.raw.lut_c = sm.lut_c;
+            tc.raw.k_grd = k_grd;
+            tc.raw.dir = vc.dir;
+            tc.max_cost = vc.max_cost;
+            tc.max_disp = smaxd;
+            const int row_off = qy * spitch + spad;
+            const uint32_t Iq = tc.col_v[row_off + qx];
+            const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
+            const double qyd = (double)qy;
+            if (flags & 2) t0 = tap_value(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+            if (flags & 4) t1 = tap_value(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+          }
+          double* slot = sm.ring + (size_t)(r % kRing) * kRingRowDoubles + (2 * gi) * kRingChain + dx;
+          slot[0] = t0;
+          slot[kRingChain] = t1;
+        }
+        __threadfence_block();
+        atomicAdd(&sm.ctl->done[r], 1);
+      }
+    } else {
+      for (int r = 0; r < WND; ++r) {
+        while (v_done[r] < row_items) __nanosleep(20);
+        __threadfence_block();
+        if (live) {
+          const volatile double* tp = sm.ring + (size_t)(r % kRing) * kRingRowDoubles + lane * kRingChain;
+#pragma unroll
+          for (int k0 = 0; k0 < WND; k0 += 12) {  // 12 loads in flight, then 12 dependent adds
+            double t[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+              if (k0 + k < WND) t[k] = tp[k0 + k];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+              if (k0 + k < WND) sum = dadd(sum, t[k]);
+          }
+          const double total = pc.cross_scale ? dadd(cost, dmul(sum, pc.scale_wgt[s])) : sum;
+          if (total >= ch_bound) live = false;  // rejected for certain: stop this chain
+        }
+        const int live_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
+        if (lane < 2 * npairs && !(lane & 1)) {
+          const int f = ch_v | (live ? 2 : 0) | (live_other ? 4 : 0);
+          if (f != sm.pd[lane >> 1].flags) *reinterpret_cast<volatile int*>(&sm.pd[lane >> 1].flags) = f;
+        }
+        __syncwarp();
+        if (lane == 0) *v_consumed = r + 1;
+      }
+    }
+    __syncthreads();
+    if (consumer && ch_on) {
+      if (pc.cross_scale) cost = dadd(cost, dmul(sum, pc.scale_wgt[s]));  // pre_cs_pc.cc:182
+      else cost = sum;
+      disp = ddiv(disp, 2.0);
+    }
+    cx /= 2;
+    cy /= 2;
+  }
+  return cost;
+}
+
 }  // namespace cspm

@@ -420,7 +420,7 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
     return e && std::string(e) == "diag";
   }();
   bool persistent = !force_diag;
-  const size_t smem_p = EngineCfg<kSpRows>::kSmemBytes;
+  const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
   int sms = 0, coop = 0, occ = 0;
   auto kern = wnd == 35 ? k_spatial_persist<35> : k_spatial_persist<0>;
   if (persistent) {

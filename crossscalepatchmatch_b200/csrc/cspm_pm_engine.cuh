@@ -9,7 +9,7 @@
 // because every pixel has only one live candidate at a time.)
 #pragma once
 
-constexpr int kSpThreads = 1024;
+constexpr int kSpThreads = 768;
 constexpr int kSpCtasPerSm = 1;
 constexpr int kSpTasks = 16;  // pixels per CTA per pass: one producer warp per pixel at least
 constexpr int kSpRows = 5;      // window rows per pipeline chunk (WND = 35)
@@ -43,7 +43,8 @@ __device__ unsigned long long g_sp_prof[8];
 template <int WND>
 __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(PcDev pc, PmDev pm, int rev, unsigned int* barrier_ctr) {
   extern __shared__ double s_dyn[];
-  const EngineSmem sm = engine_smem<kSpRows>(s_dyn);
+  const EngineSmem sm = engine_smem<kSpRows>(s_dyn);   // chunked pipeline (generic window size)
+  const RingSmem rs = ring_smem(s_dyn);                // ring pipeline (WND == 35); same LUT placement
   stage_luts(pc, sm.lut_w, sm.lut_c);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool consumer = warp == kSpThreads / 32 - 1;
@@ -90,7 +91,9 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
       // both candidates must beat the pixel's cost at the start of the step (cs_patchmatch.cc:201,209)
       const double ch_bound = __shfl_sync(0xffffffffu, ch_min, lane & ~1);
       SP_PROF(0);
-      const double ch_cost = engine_eval_pairs<WND, kSpRows, kSpThreads>(pc, sm, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound);
+      const double ch_cost = WND == 35
+          ? engine_eval_pairs_ring<kSpThreads>(pc, rs, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound)
+          : engine_eval_pairs<WND, kSpRows, kSpThreads>(pc, sm, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound);
       SP_PROF(1);
       // acceptance in the reference's order: x-axis neighbour, then y-axis neighbour (:198-212)
       if (consumer) {
