@@ -432,7 +432,7 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   }
   if (persistent) {
     // one cooperative launch per sweep; the grid barrier needs every CTA resident
-    CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int), pm->stream));
+    CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, pm->stream));
     int rev_arg = rev;
     unsigned int* bar = pm->grid_barrier;
     void* args[] = {&pcd, &d, &rev_arg, &bar};
@@ -544,7 +544,7 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
       pm->win = pm->arena.alloc<unsigned int>(n);
       pm->dis_tmp = pm->arena.alloc<uint8_t>(n);
       pm->tap_counter = pm->arena.alloc<unsigned long long>(1);
-      pm->grid_barrier = pm->arena.alloc<unsigned int>(1);
+      pm->grid_barrier = pm->arena.alloc<unsigned int>(32 * 1024);  // one 128-B line per CTA
       CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(unsigned long long), pm->stream));
       CSPM_CUDA(cudaStreamSynchronize(pm->stream));
       return pm;
