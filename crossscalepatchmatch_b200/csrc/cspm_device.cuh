@@ -29,7 +29,7 @@ struct ScaleDev {
   int pad, pitch;              // elements; row r, column x lives at r*pitch + pad + x
   const uint32_t* color[2];    // B | G<<8 | R<<16 (8-bit originals; byte 3 = 0)
   const double* grad[2];       // Sobel-x of float gray, f64 (cc/grd_cc.cpp:70-77)
-  const uint4* census[2];      // 80-bit census codes in the low 80 bits (CEN only)
+  const uint32_t* cen_hi[2];   // CEN only: bits 64..79 of the 80-bit census code; bits 0..63 live in grad[] (as raw u64)
   double max_cost[2];          // max over the whole raw cost volume, pre_ss_pc.cc:51-58
 };
 
@@ -153,10 +153,12 @@ __host__ __device__ __forceinline__ uint64_t stream_refine(int h, int n_ref, int
 // on the integer L1 distance of two 8-bit pixels, so it is a 32-entry table.
 struct RawCtx {
   const uint32_t* col_o;  // other view, padded
-  const double* grd_o;
+  const double* grd_o;    // GRD: x-gradient; CEN: census bits 0..63 (raw u64 stored in the f64 slot)
+  const uint32_t* hi_o;   // CEN: census bits 64..79
   const double* lut_c;
   double k_grd;
   int dir;  // partner x = q_x + dir*d : -1 for the left view, +1 for the right view
+  int w;    // CEN: image width (partner outside the image costs CENCUS_BIT)
 };
 // min(|x|, TAU_GRD) as the reference's `grdDiff > TAU_GRD ? TAU_GRD : grdDiff` (no NaN handling needed:
 // inputs are finite), cheaper than fmin(), which must honour NaN semantics.
@@ -164,8 +166,19 @@ __device__ __forceinline__ double abs_min2(double x) {
   const double ax = fabs(x);
   return ax > 2.0 ? 2.0 : ax;
 }
-__device__ __forceinline__ double raw_grd(const RawCtx& r, int row_off, int qx, uint32_t cq, double gq, int d) {
-  const int idx = row_off + qx + r.dir * d;
+// CC = CC_GRD: cq = packed colour of q, gq = gradient of q (qhi unused).
+// CC = CC_CEN: CenCC raw cost (cc/cen_cc.cc:48-67 / :116-135): Hamming distance of the 80-bit census
+// codes, CENCUS_BIT = 80 when the partner lies outside the image; gq carries code bits 0..63, qhi bits 64..79.
+template <int CC>
+__device__ __forceinline__ double raw_cost(const RawCtx& r, int row_off, int qx, uint32_t cq, double gq, uint32_t qhi, int d) {
+  const int px = qx + r.dir * d;
+  const int idx = row_off + px;
+  if (CC == CC_CEN) {
+    if (px < 0 || px >= r.w) return 80.0;
+    const unsigned long long lo = (unsigned long long)__double_as_longlong(gq) ^ (unsigned long long)__double_as_longlong(r.grd_o[idx]);
+    const uint32_t hi = (qhi ^ r.hi_o[idx]) & 0xFFFFu;
+    return (double)(__popcll(lo) + __popc(hi));
+  }
   const uint32_t cp = r.col_o[idx];
   const double gp = r.grd_o[idx];
   const int sad = min((int)__vsadu4(cq, cp), kLutC - 1);
@@ -178,12 +191,14 @@ __device__ __forceinline__ double raw_grd(const RawCtx& r, int row_off, int qx, 
 struct TapCtx {
   const uint32_t* col_v;  // this view, padded
   const double* grd_v;
+  const uint32_t* hi_v;   // CEN only
   const double* lut_w;
   RawCtx raw;
   double max_cost;
   int max_disp;
 };
 // the plane-dependent part: wgt * (max_cost | lerp of the two raw costs)
+template <int CC>
 __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double wgt, double a,
                                             double q_disp_y) {
   const double q_disp = dadd(dmul(a, (double)qx), q_disp_y);
@@ -191,16 +206,18 @@ __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx
   if (fl <= 0 || fl >= t.max_disp) return dmul(wgt, t.max_cost);
   const double fw = dsub((double)(fl + 1), q_disp);
   const double gq = t.grd_v[row_off + qx];
-  const double c0 = raw_grd(t.raw, row_off, qx, Iq, gq, fl);
-  const double c1 = raw_grd(t.raw, row_off, qx, Iq, gq, fl + 1);
+  const uint32_t qhi = CC == CC_CEN ? t.hi_v[row_off + qx] : 0u;
+  const double c0 = raw_cost<CC>(t.raw, row_off, qx, Iq, gq, qhi, fl);
+  const double c1 = raw_cost<CC>(t.raw, row_off, qx, Iq, gq, qhi, fl + 1);
   const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
   return dmul(wgt, tmp);
 }
+template <int CC>
 __device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx, uint32_t Ip, double a,
                                            double q_disp_y) {
   const uint32_t Iq = t.col_v[row_off + qx];
   const double wgt = t.lut_w[__vsadu4(Ip, Iq)];
-  return tap_value(t, row_off, qx, Iq, wgt, a, q_disp_y);
+  return tap_value<CC>(t, row_off, qx, Iq, wgt, a, q_disp_y);
 }
 
 __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, const double* lut_w,
@@ -209,9 +226,12 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
   TapCtx t;
   t.col_v = sc.color[v];
   t.grd_v = sc.grad[v];
+  t.hi_v = sc.cen_hi[v];
   t.lut_w = lut_w;
   t.raw.col_o = sc.color[1 - v];
   t.raw.grd_o = sc.grad[1 - v];
+  t.raw.hi_o = sc.cen_hi[1 - v];
+  t.raw.w = sc.w;
   t.raw.lut_c = lut_c;
   t.raw.k_grd = pc.k_grd;
   t.raw.dir = v == 0 ? -1 : 1;
@@ -230,6 +250,7 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 // as the final expression — has reached `bound`, the answer is "no" whatever
 // the remaining taps add, and the (partial) value returned is still >= bound.
 // Pass bound = +inf to get the full sum.  Checked once per window row.
+template <int CC>
 __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int rx, int ry, double a, double b,
                                               double c, const double* lut_w, const double* lut_c, double bound,
                                               double cost_prev, double w_s) {
@@ -243,7 +264,7 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
   for (int qy = y0; qy <= y1; ++qy) {
     const double q_disp_y = dadd(dmul(b, (double)qy), c);
     const int row_off = qy * sc.pitch + sc.pad;
-    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term(t, row_off, qx, Ip, a, q_disp_y));
+    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC>(t, row_off, qx, Ip, a, q_disp_y));
     const double total = pc.cross_scale ? dadd(cost_prev, dmul(cost, w_s)) : cost;
     if (total >= bound) break;
   }
@@ -253,16 +274,17 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
 // IPlaneCost::GetPlaneCost: PreSSPC (pre_ss_pc.cc:74-118) or PreCSPC
 // (pre_cs_pc.cc:133-188).  Returns the exact cost if it is < bound, otherwise
 // some value >= bound (see window_cost).
+template <int CC>
 __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int ry, const PlaneD& p,
                                              const double* lut_w, const double* lut_c, double bound) {
-  if (!pc.cross_scale) return window_cost(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
+  if (!pc.cross_scale) return window_cost<CC>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);
   int cx = rx, cy = ry;
   for (int s = 0; s < pc.scale_num; ++s) {
     PlaneD q = p;
     update_param(q, (double)cx, (double)cy, cur_disp);
-    const double sc_cost = window_cost(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
+    const double sc_cost = window_cost<CC>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
     cost = dadd(cost, dmul(sc_cost, pc.scale_wgt[s]));
     if (cost >= bound) break;
     cy /= 2;
@@ -349,7 +371,7 @@ struct PairDesc {  // 64 B, written by the consumer lanes, read (broadcast) by t
   int flags;  // bit0: view, bit1: chain 2p on, bit2: chain 2p+1 on
 };
 
-template <int WND, int ROWS, int NT>
+template <int CC, int WND, int ROWS, int NT>
 __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const EngineSmem& sm, int nch, bool ch_on, int ch_v,
                                                     int ch_x, int ch_y, const PlaneD& ch_plane, double ch_bound) {
   constexpr int kStride = EngineCfg<ROWS>::kStride;
@@ -390,6 +412,8 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
     const uint32_t* col1 = sc.color[1];
     const double* grd0 = sc.grad[0];
     const double* grd1 = sc.grad[1];
+    const uint32_t* hi0 = sc.cen_hi[0];
+    const uint32_t* hi1 = sc.cen_hi[1];
     const bool prof = blockIdx.x == gridDim.x / 2 && lane == 0;
     const long long loop_t0 = clock64();
     for (int ci = 0; ci <= nchunks; ++ci) {
@@ -413,9 +437,12 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
               TapCtx tc;
               tc.col_v = v ? col1 : col0;
               tc.grd_v = v ? grd1 : grd0;
+              tc.hi_v = v ? hi1 : hi0;
               tc.lut_w = sm.lut_w;
               tc.raw.col_o = v ? col0 : col1;
               tc.raw.grd_o = v ? grd0 : grd1;
+              tc.raw.hi_o = v ? hi0 : hi1;
+              tc.raw.w = sc.w;
               tc.raw.lut_c = sm.lut_c;
               tc.raw.k_grd = pc.k_grd;
               tc.raw.dir = v ? 1 : -1;
@@ -425,8 +452,8 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
               const uint32_t Iq = tc.col_v[row_off + qx];
               const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
               const double qyd = (double)qy;
-              if (flags & 2) t0 = tap_value(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
-              if (flags & 4) t1 = tap_value(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+              if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+              if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
             }
             buf[(2 * gi) * kStride + kk] = t0;
             buf[(2 * gi + 1) * kStride + kk] = t1;
@@ -490,6 +517,8 @@ struct ViewCtx {     // everything a producer needs about (scale, view), copied 
   const double* grd_v;    // dynamically indexed constant-bank loads
   const uint32_t* col_o;
   const double* grd_o;
+  const uint32_t* hi_v;   // CEN only
+  const uint32_t* hi_o;
   double max_cost;
   int dir, pad_;
 };
@@ -519,7 +548,7 @@ __device__ __forceinline__ RingSmem ring_smem(double* dyn) {
   return e;
 }
 
-template <int NT>
+template <int CC, int NT>
 __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const RingSmem& sm, int nch, bool ch_on, int ch_v,
                                                          int ch_x, int ch_y, const PlaneD& ch_plane, double ch_bound) {
   constexpr int WND = 35, HW = 17;
@@ -557,6 +586,7 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
         ViewCtx& vc = sm.ctl->view[lane];
         vc.col_v = sc.color[lane]; vc.grd_v = sc.grad[lane];
         vc.col_o = sc.color[1 - lane]; vc.grd_o = sc.grad[1 - lane];
+        vc.hi_v = sc.cen_hi[lane]; vc.hi_o = sc.cen_hi[1 - lane];
         vc.max_cost = sc.max_cost[lane];
         vc.dir = lane ? 1 : -1;
       }
@@ -588,9 +618,12 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
             TapCtx tc;
             tc.col_v = vc.col_v;
             tc.grd_v = vc.grd_v;
+            tc.hi_v = vc.hi_v;
             tc.lut_w = sm.lut_w;
             tc.raw.col_o = vc.col_o;
             tc.raw.grd_o = vc.grd_o;
+            tc.raw.hi_o = vc.hi_o;
+            tc.raw.w = sw;
             tc.raw.lut_c = sm.lut_c;
             tc.raw.k_grd = k_grd;
             tc.raw.dir = vc.dir;
@@ -600,8 +633,8 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
             const uint32_t Iq = tc.col_v[row_off + qx];
             const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
             const double qyd = (double)qy;
-            if (flags & 2) t0 = tap_value(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
-            if (flags & 4) t1 = tap_value(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+            if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+            if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
           }
           double* slot = sm.ring + (size_t)(r % kRing) * kRingRowDoubles + (2 * gi) * kRingChain + dx;
           slot[0] = t0;

@@ -43,6 +43,7 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 }
 
 // ------------------------------------------------------------------- init
+template <int CC>
 __global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
   __shared__ double s_lut_w[kLutW];
   __shared__ double s_lut_c[kLutC];
@@ -61,11 +62,12 @@ __global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
   PlaneD p;
   p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
   update_param(p, (double)x, (double)y, z);
-  const double cost = plane_cost(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
+  const double cost = plane_cost<CC>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
   store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
 }
 
 // ----------------------------------------------------------------- refine
+template <int CC>
 __global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
   __shared__ double s_lut_w[kLutW];
   __shared__ double s_lut_c[kLutC];
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
     const double inv = ddiv(1.0, denom);
     q.nx = dmul(q.nx, inv); q.ny = dmul(q.ny, inv); q.nz = dmul(q.nz, inv);
     update_param(q, (double)x, (double)y, z);
-    const double cost = plane_cost(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
+    const double cost = plane_cost<CC>(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
     if (cost < cur_cost) {
       cur = q;
       cur_cost = cost;
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
 // phase 1 computes every window tap's addend in parallel, phase 2 adds them
 // in the reference's row-major order (one thread per candidate), so the sum
 // is rounded exactly like the scalar loop.
+template <int CC>
 __global__ void __launch_bounds__(128) k_spatial_diag(PcDev pc, PmDev pm, int diag, int u_lo, int rev) {
   extern __shared__ double s_dyn[];
   double* s_lut_w = s_dyn;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(128) k_spatial_diag(PcDev pc, PmDev pm, int di
       double term = 0.0;  // +0.0 is the additive identity for these non-negative sums
       if (qy >= 0 && qy < sc.h && qx >= 0 && qx < sc.w) {
         const double q_disp_y = dadd(dmul(q[c].b, (double)qy), q[c].c);
-        term = tap_term(tc, qy * sc.pitch + sc.pad, qx, Ip, q[c].a, q_disp_y);
+        term = tap_term<CC>(tc, qy * sc.pitch + sc.pad, qx, Ip, q[c].a, q_disp_y);
       }
       s_terms[k] = term;
     }
@@ -207,6 +210,7 @@ __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, in
   *q = o;
   update_param(*q, (double)*cor_x, (double)y, disp);
 }
+template <int CC>
 __global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
   __shared__ double s_lut_w[kLutW];
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, do
     view_candidate(pm, v, x, y, &q, &cor_x);
     // a proposal can only win if it beats the target's cost at the start of this pass
     const double bound = pm.st[v][6 * (size_t)pm.w * pm.h + (size_t)y * pm.w + cor_x];
-    const double cost = plane_cost(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
+    const double cost = plane_cost<CC>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;
     cand_tx[i] = cor_x;
@@ -396,7 +400,8 @@ static void check_pair(const cspm_pm* pm, const cspm_pc* pc) {
 
 static void run_init(cspm_pm* pm, const cspm_pc* pc) {
   dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
-  k_init<<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
+  if (pc->dev.cc_kind == CC_CEN) k_init<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
+  else k_init<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
@@ -404,7 +409,8 @@ static void run_init(cspm_pm* pm, const cspm_pc* pc) {
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
   dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
-  k_refine<<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  if (pc->dev.cc_kind == CC_CEN) k_refine<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  else k_refine<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
@@ -422,7 +428,8 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   bool persistent = !force_diag;
   const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
   int sms = 0, coop = 0, occ = 0;
-  auto kern = wnd == 35 ? k_spatial_persist<35> : k_spatial_persist<0>;
+  auto kern = pcd.cc_kind == CC_CEN ? (wnd == 35 ? k_spatial_persist<CC_CEN, 35> : k_spatial_persist<CC_CEN, 0>)
+                                    : (wnd == 35 ? k_spatial_persist<CC_GRD, 35> : k_spatial_persist<CC_GRD, 0>);
   if (persistent) {
     CSPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pm->device));
     CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm->device));
@@ -443,7 +450,8 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
     for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
       const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
       dim3 g(u_hi - u_lo + 1, 2);
-      k_spatial_diag<<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
+      if (pcd.cc_kind == CC_CEN) k_spatial_diag<CC_CEN><<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
+      else k_spatial_diag<CC_GRD><<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
       pm->stats.kernel_launches++;
     }
   }
@@ -461,7 +469,8 @@ static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
   for (int v = 0; v < 2; ++v) {
     k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
     dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8);
-    k_view_eval<<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    if (pc->dev.cc_kind == CC_CEN) k_view_eval<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    else k_view_eval<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
     dim3 g1((pm->w + 127) / 128, pm->h);
     k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
     k_view_commit<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->win);

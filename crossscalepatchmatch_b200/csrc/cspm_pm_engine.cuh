@@ -29,7 +29,7 @@ __device__ unsigned long long g_sp_prof[8];
     }                                                              \
   } while (0)
 
-template <int WND>
+template <int CC, int WND>
 __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(PcDev pc, PmDev pm, int rev, unsigned int* barrier_ctr) {
   extern __shared__ double s_dyn[];
   const EngineSmem sm = engine_smem<kSpRows>(s_dyn);   // chunked pipeline (generic window size)
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
       const double ch_bound = __shfl_sync(0xffffffffu, ch_min, lane & ~1);
       SP_PROF(0);
       const double ch_cost = WND == 35
-          ? engine_eval_pairs_ring<kSpThreads>(pc, rs, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound)
-          : engine_eval_pairs<WND, kSpRows, kSpThreads>(pc, sm, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound);
+          ? engine_eval_pairs_ring<CC, kSpThreads>(pc, rs, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound)
+          : engine_eval_pairs<CC, WND, kSpRows, kSpThreads>(pc, sm, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound);
       SP_PROF(1);
       // acceptance in the reference's order: x-axis neighbour, then y-axis neighbour (:198-212)
       if (consumer) {

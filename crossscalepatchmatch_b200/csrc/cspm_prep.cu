@@ -110,9 +110,67 @@ __global__ void k_pyrdown(const uint8_t* __restrict__ src, int w, int h, uint8_t
   o[2] = (uint8_t)((sum[2] + 128) >> 8);
 }
 
+// CenCC (cc/cen_cc.cc:4-47): 8-bit gray (OpenCV 2.4.8 RGB2Gray<uchar>: 14-bit fixed point) and the
+// 9x9 census transform with WRAP-AROUND window borders; bit k of the 80-bit code, k counting the
+// window positions row-major without the centre, is (centre > neighbour).
+__device__ __forceinline__ uint8_t gray8(int r, int g, int b) { return (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14); }
+__global__ void k_gray8_bgr(const uint8_t* __restrict__ bgr, int n, uint8_t* __restrict__ gray) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gray[i] = gray8(bgr[3 * i + 2], bgr[3 * i + 1], bgr[3 * i]);
+}
+__global__ void k_census(const uint8_t* __restrict__ gray, int w, int h, int pad, int pitch,
+                         unsigned long long* __restrict__ lo, uint32_t* __restrict__ hi) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t c = gray[(size_t)y * w + x];
+  unsigned long long l = 0;
+  uint32_t hbits = 0;
+  int k = 0;
+  for (int wy = -4; wy <= 4; ++wy) {
+    const int qy = (y + wy + h) % h;
+    for (int wx = -4; wx <= 4; ++wx) {
+      if (wy == 0 && wx == 0) continue;
+      const int qx = (x + wx + w) % w;
+      const unsigned long long bit = c > gray[(size_t)qy * w + qx] ? 1ull : 0ull;
+      if (k < 64) l |= bit << k;
+      else hbits |= (uint32_t)bit << (k - 64);
+      ++k;
+    }
+  }
+  const size_t o = (size_t)y * pitch + pad + x;
+  lo[o] = l;
+  hi[o] = hbits;
+}
+// buildCV / buildRightCV export for CenCC on arbitrary CV_64FC3 input: convertTo(CV_8U) is
+// saturate_cast<uchar>(cvRound(v)) (round half to even), cen_cc.cc:13-17.
+__global__ void k_gray8_f64(const double* __restrict__ rgb, int n, uint8_t* __restrict__ gray) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ch[3];
+  for (int k = 0; k < 3; ++k) ch[k] = min(max(__double2int_rn(rgb[3 * i + k]), 0), 255);
+  gray[i] = gray8(ch[0], ch[1], ch[2]);
+}
+__global__ void k_build_cv_cen(const unsigned long long* __restrict__ llo, const uint32_t* __restrict__ lhi,
+                               const unsigned long long* __restrict__ rlo, const uint32_t* __restrict__ rhi, int w, int h,
+                               int right_view, double* __restrict__ vol) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, d = blockIdx.z;
+  if (x >= w) return;
+  const size_t row = (size_t)y * w;
+  double c = 80.0;  // CENCUS_BIT
+  if (!right_view) {
+    if (x - d >= 0) c = (double)(__popcll(llo[row + x] ^ rlo[row + x - d]) + __popc((lhi[row + x] ^ rhi[row + x - d]) & 0xFFFFu));
+  } else {
+    if (x + d < w) c = (double)(__popcll(rlo[row + x] ^ llo[row + x + d]) + __popc((rhi[row + x] ^ lhi[row + x + d]) & 0xFFFFu));
+  }
+  vol[((size_t)d * h + y) * w + x] = c;
+}
+
 // K2: max over the whole raw cost volume d in [0, max_disp], all pixels
 // (replaces the minMaxLoc loop pre_ss_pc.cc:51-58).  Costs are >= 0, so the
 // f64 bit pattern orders like an unsigned integer.
+template <int CC>
 __global__ void k_max_raw_cost(PcDev pc, int s, int v, unsigned long long* out_bits) {
   __shared__ double s_lut_c[kLutC];
   for (int i = threadIdx.x; i < kLutC; i += blockDim.x) s_lut_c[i] = pc.lut_c[i];
@@ -126,13 +184,15 @@ __global__ void k_max_raw_cost(PcDev pc, int s, int v, unsigned long long* out_b
     const int row_off = y * sc.pitch + sc.pad;
     const uint32_t cq = t.col_v[row_off + x];
     const double gq = t.grd_v[row_off + x];
-    for (int d = 0; d <= sc.max_disp; ++d) m = fmax(m, raw_grd(t.raw, row_off, x, cq, gq, d));
+    const uint32_t qhi = CC == CC_CEN ? t.hi_v[row_off + x] : 0u;
+    for (int d = 0; d <= sc.max_disp; ++d) m = fmax(m, raw_cost<CC>(t.raw, row_off, x, cq, gq, qhi, d));
   }
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
 }
 
 // K3: batched IPlaneCost::GetPlaneCost, one thread per query.
+template <int CC>
 __global__ void k_plane_cost_batch(PcDev pc, int n, const int* __restrict__ x, const int* __restrict__ y,
                                    const double* __restrict__ normal, const double* __restrict__ point,
                                    const int* __restrict__ view, double* __restrict__ out) {
@@ -144,7 +204,7 @@ __global__ void k_plane_cost_batch(PcDev pc, int n, const int* __restrict__ x, c
   PlaneD p;
   p.nx = normal[3 * i]; p.ny = normal[3 * i + 1]; p.nz = normal[3 * i + 2];
   update_param(p, point[3 * i], point[3 * i + 1], point[3 * i + 2]);
-  out[i] = plane_cost(pc, view[i], x[i], y[i], p, s_lut_w, s_lut_c, CUDART_INF);
+  out[i] = plane_cost<CC>(pc, view[i], x[i], y[i], p, s_lut_w, s_lut_c, CUDART_INF);
 }
 
 // buildCV / buildRightCV export for arbitrary CV_64FC3 input (cc/grd_cc.cpp:60-154).
@@ -265,7 +325,6 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
   CSPM_REQUIRE(max_disp >= 1, "max_disp must be >= 1");
   CSPM_REQUIRE(wnd_size >= 1 && wnd_size <= 63, "wnd_size out of range [1,63]");
   CSPM_REQUIRE(!cross_scale || (scale_num >= 2 && scale_num <= kMaxScales), "scale_num out of range [2,8]");
-  if (cc->kind != CC_GRD) throw Error(CSPM_EUNSUPPORTED, "cc_method " + cc->name + " has no CUDA path yet (GRD only)");
   use_device(device);
 
   cspm_pc* pc = new cspm_pc();
@@ -331,7 +390,17 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
         pc->stats.kernel_launches++;
         S.color[v] = color;
         S.grad[v] = grad;
-        S.census[v] = nullptr;
+        S.cen_hi[v] = nullptr;
+        if (cc->kind == CC_CEN) {  // census code: bits 0..63 replace the gradient array, bits 64..79 in cen_hi
+          uint8_t* g8 = pc->arena.alloc<uint8_t>((size_t)sw * sh);
+          uint32_t* hi = pc->arena.alloc<uint32_t>((size_t)S.pitch * sh);
+          CSPM_CUDA(cudaMemsetAsync(hi, 0, sizeof(uint32_t) * (size_t)S.pitch * sh, st));
+          k_gray8_bgr<<<(sw * sh + 255) / 256, 256, 0, st>>>(pc->d_bgr[v][s], sw * sh, g8);
+          dim3 gc((sw + 127) / 128, sh);
+          k_census<<<gc, 128, 0, st>>>(g8, sw, sh, S.pad, S.pitch, reinterpret_cast<unsigned long long*>(grad), hi);
+          pc->stats.kernel_launches += 2;
+          S.cen_hi[v] = hi;
+        }
       }
     }
     CSPM_CUDA(cudaGetLastError());
@@ -342,7 +411,8 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     for (int s = 0; s < pc->scale_num; ++s)
       for (int v = 0; v < 2; ++v) {
         dim3 g((D.sc[s].w + 127) / 128, D.sc[s].h);
-        k_max_raw_cost<<<g, 128, 0, st>>>(D, s, v, d_max + v * kMaxScales + s);
+        if (cc->kind == CC_CEN) k_max_raw_cost<CC_CEN><<<g, 128, 0, st>>>(D, s, v, d_max + v * kMaxScales + s);
+        else k_max_raw_cost<CC_GRD><<<g, 128, 0, st>>>(D, s, v, d_max + v * kMaxScales + s);
         pc->stats.kernel_launches++;
       }
     CSPM_CUDA(cudaGetLastError());
@@ -431,13 +501,32 @@ int cspm_cc_build_cv(const cspm_cc_t* cc, const double* l_rgb, const double* r_r
   return guard([&] {
     CSPM_REQUIRE(cc && l_rgb && r_rgb && cost_vol, "null argument");
     CSPM_REQUIRE(w > 0 && h > 0 && max_dis > 0, "bad geometry");
-    if (cc->kind != CC_GRD) throw Error(CSPM_EUNSUPPORTED, "cc_method " + cc->name + " has no CUDA path yet (GRD only)");
     use_device(device);
     DeviceArena A;
     try {
       const size_t n = (size_t)w * h;
       double* d_l = A.alloc<double>(3 * n);
       double* d_r = A.alloc<double>(3 * n);
+      if (cc->kind == CC_CEN) {
+        uint8_t* g8 = A.alloc<uint8_t>(n);
+        unsigned long long* lo[2] = {A.alloc<unsigned long long>(n), A.alloc<unsigned long long>(n)};
+        uint32_t* hi[2] = {A.alloc<uint32_t>(n), A.alloc<uint32_t>(n)};
+        double* d_vol = A.alloc<double>(n * max_dis);
+        CSPM_CUDA(cudaMemcpy(d_l, l_rgb, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+        CSPM_CUDA(cudaMemcpy(d_r, r_rgb, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+        dim3 gc((w + 127) / 128, h);
+        for (int v = 0; v < 2; ++v) {
+          k_gray8_f64<<<(unsigned)((n + 255) / 256), 256>>>(v == 0 ? d_l : d_r, (int)n, g8);
+          k_census<<<gc, 128>>>(g8, w, h, 0, w, lo[v], hi[v]);
+        }
+        dim3 gv((w + 127) / 128, h, max_dis);
+        k_build_cv_cen<<<gv, 128>>>(lo[0], hi[0], lo[1], hi[1], w, h, right_view, d_vol);
+        CSPM_CUDA(cudaGetLastError());
+        CSPM_CUDA(cudaMemcpy(cost_vol, d_vol, sizeof(double) * n * max_dis, cudaMemcpyDeviceToHost));
+        CSPM_CUDA(cudaDeviceSynchronize());
+        A.release();
+        return;
+      }
       float* d_gray = A.alloc<float>(n);
       double* d_lg = A.alloc<double>(n);
       double* d_rg = A.alloc<double>(n);
@@ -513,7 +602,8 @@ int cspm_pc_get_plane_cost(const cspm_pc_t* pc, int n, const int* x, const int* 
       CSPM_CUDA(cudaMemcpyAsync(d_v, view, sizeof(int) * n, cudaMemcpyHostToDevice, st));
       CSPM_CUDA(cudaMemcpyAsync(d_n, normal_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
       CSPM_CUDA(cudaMemcpyAsync(d_p, point_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
-      k_plane_cost_batch<<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o);
+      if (pc->dev.cc_kind == CC_CEN) k_plane_cost_batch<CC_CEN><<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o);
+      else k_plane_cost_batch<CC_GRD><<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o);
       CSPM_CUDA(cudaGetLastError());
       pc->stats.kernel_launches++;
       pc->stats.plane_evals += n;

@@ -88,6 +88,56 @@ def test_build_cv(cspm, orc_lib, pair, right):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("right", [0, 1])
+def test_build_cv_census(cspm, orc_lib, pair, right):
+    l, r = pair
+    rng = np.random.default_rng(3)
+    # CV_64FC3 input with fractional values: convertTo(CV_8U) rounds half to even and saturates (cen_cc.cc:13)
+    lrgb = l[..., ::-1].astype(np.float64) + rng.choice([0.0, 0.5, -0.5, 0.25], size=l.shape)
+    rrgb = r[..., ::-1].astype(np.float64) + rng.choice([0.0, 0.5, 300.0, -7.0], size=r.shape, p=[0.9, 0.06, 0.02, 0.02])
+    cc = cspm.CenCC()
+    got = cc.buildRightCV(lrgb, rrgb, D + 1) if right else cc.buildCV(lrgb, rrgb, D + 1)
+    want = orc_lib.build_cv("CEN", lrgb, rrgb, D + 1, right)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (3, 0.3)])
+def test_census_plane_cost_and_patchmatch(cspm, orc_lib, pair, S, lam):
+    """cc_name=CEN (CenCC, cc/cen_cc.cc): the cost every input.txt line of the reference uses."""
+    l, r = pair
+    cc = cspm.GetCCType("CEN")
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam, cc_name="CEN")
+    pg = cspm.PreSSPC(l, r, D, 35, cc) if S == 0 else cspm.PreCSPC(l, r, D, 35, S, cc, lam)
+    for a, b in zip(po.info(), pg.info()):
+        assert np.array_equal(a, b)
+    assert po.info()[1].max() == 80.0
+    x, y, nm, pt, v = _queries(np.random.default_rng(2), W, H, D, 3000)
+    assert np.array_equal(po.get_plane_cost(x, y, nm, pt, v), pg.GetPlaneCostBatch(x, y, nm, pt, v))
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=21)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=21)
+    mo.patchmatch(2, po, True)
+    mg.PatchMatch(2, pg, True)
+    _same_state(mo, mg, "census full run")
+    for view in (0, 1):
+        assert np.array_equal(mo.dis(view), mg.dis(view))
+
+
+@pytest.mark.parametrize("wnd", [5, 11, 21, 41])
+def test_other_window_sizes(cspm, orc_lib, wnd):
+    """wnd_size is a constructor argument of PreSSPC/PreCSPC (main.cc fixes 35): the generic-window
+    code paths (runtime window size in every kernel, chunked pipeline in the spatial sweep)."""
+    w, h, d = 70, 44, 14
+    l, r, _ = make_pair(w, h, d, 500 + wnd)
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, d, wnd, 3, 0.3)
+    pg = cspm.PreCSPC(l, r, d, wnd, 3, cc, 0.3)
+    mo = orc.PatchMatch(orc_lib, l, r, d, 4, seed=5)
+    mg = cspm.CSPatchMatch(l, r, d, 4, seed=5)
+    mo.patchmatch(2, po, False)
+    mg.PatchMatch(2, pg, False)
+    _same_state(mo, mg, f"wnd={wnd}")
+
+
 def _same_state(a, b, what):
     for view in (0, 1):
         for name, x, y in zip(("normal", "param", "min_cost"), a.planes(view), b.planes(view)):
