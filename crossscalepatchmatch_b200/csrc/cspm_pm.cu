@@ -43,11 +43,13 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 }
 
 // ------------------------------------------------------------------- init
+constexpr int kBulkBy = 16;  // bulk kernels: 32 x 16 pixels per CTA, one CTA per SM (98 KB replicated table)
 template <int CC>
-__global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
-  __shared__ double s_lut_w[kLutW];
-  __shared__ double s_lut_c[kLutC];
-  stage_luts(pc, s_lut_w, s_lut_c);
+__global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
+  extern __shared__ double s_dyn[];
+  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
+  stage_luts_rep(pc, s_dyn, s_lut_c);
+  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int v = blockIdx.z;
@@ -62,16 +64,17 @@ __global__ void __launch_bounds__(256) k_init(PcDev pc, PmDev pm) {
   PlaneD p;
   p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
   update_param(p, (double)x, (double)y, z);
-  const double cost = plane_cost<CC>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
+  const double cost = plane_cost<CC, kLutRepShift>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
   store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
 }
 
 // ----------------------------------------------------------------- refine
 template <int CC>
-__global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
-  __shared__ double s_lut_w[kLutW];
-  __shared__ double s_lut_c[kLutC];
-  stage_luts(pc, s_lut_w, s_lut_c);
+__global__ void __launch_bounds__(32 * kBulkBy, 1) k_refine(PcDev pc, PmDev pm, int iter) {
+  extern __shared__ double s_dyn[];
+  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
+  stage_luts_rep(pc, s_dyn, s_lut_c);
+  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int v = blockIdx.z;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) k_refine(PcDev pc, PmDev pm, int iter) {
     const double inv = ddiv(1.0, denom);
     q.nx = dmul(q.nx, inv); q.ny = dmul(q.ny, inv); q.nz = dmul(q.nz, inv);
     update_param(q, (double)x, (double)y, z);
-    const double cost = plane_cost<CC>(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
+    const double cost = plane_cost<CC, kLutRepShift>(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
     if (cost < cur_cost) {
       cur = q;
       cur_cost = cost;
@@ -211,11 +214,12 @@ __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, in
   update_param(*q, (double)*cor_x, (double)y, disp);
 }
 template <int CC>
-__global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
+__global__ void __launch_bounds__(32 * kBulkBy, 1) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
-  __shared__ double s_lut_w[kLutW];
-  __shared__ double s_lut_c[kLutC];
-  stage_luts(pc, s_lut_w, s_lut_c);
+  extern __shared__ double s_dyn[];
+  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
+  stage_luts_rep(pc, s_dyn, s_lut_c);
+  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   unsigned long long taps = 0;
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) k_view_eval(PcDev pc, PmDev pm, int v, do
     view_candidate(pm, v, x, y, &q, &cor_x);
     // a proposal can only win if it beats the target's cost at the start of this pass
     const double bound = pm.st[v][6 * (size_t)pm.w * pm.h + (size_t)y * pm.w + cor_x];
-    const double cost = plane_cost<CC>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
+    const double cost = plane_cost<CC, kLutRepShift>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;
     cand_tx[i] = cor_x;
@@ -398,19 +402,34 @@ static void check_pair(const cspm_pm* pm, const cspm_pc* pc) {
   CSPM_REQUIRE(pc->dims[0][0] == pm->w && pc->dims[0][1] == pm->h, "plane cost and patch match image sizes differ");
 }
 
+template <typename K>
+static void bulk_smem(K kern) {
+  CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes));
+}
+
 static void run_init(cspm_pm* pm, const cspm_pc* pc) {
-  dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
-  if (pc->dev.cc_kind == CC_CEN) k_init<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
-  else k_init<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm));
+  dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
+  if (pc->dev.cc_kind == CC_CEN) {
+    bulk_smem(k_init<CC_CEN>);
+    k_init<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm));
+  } else {
+    bulk_smem(k_init<CC_GRD>);
+    k_init<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm));
+  }
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
 }
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
-  dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8, 2);
-  if (pc->dev.cc_kind == CC_CEN) k_refine<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
-  else k_refine<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
+  if (pc->dev.cc_kind == CC_CEN) {
+    bulk_smem(k_refine<CC_CEN>);
+    k_refine<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  } else {
+    bulk_smem(k_refine<CC_GRD>);
+    k_refine<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter);
+  }
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
@@ -468,9 +487,14 @@ static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const size_t n = (size_t)pm->w * pm->h;
   for (int v = 0; v < 2; ++v) {
     k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
-    dim3 b(32, 8), g((pm->w + 31) / 32, (pm->h + 7) / 8);
-    if (pc->dev.cc_kind == CC_CEN) k_view_eval<CC_CEN><<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
-    else k_view_eval<CC_GRD><<<g, b, 0, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy);
+    if (pc->dev.cc_kind == CC_CEN) {
+      bulk_smem(k_view_eval<CC_CEN>);
+      k_view_eval<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    } else {
+      bulk_smem(k_view_eval<CC_GRD>);
+      k_view_eval<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
+    }
     dim3 g1((pm->w + 127) / 128, pm->h);
     k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
     k_view_commit<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->win);
