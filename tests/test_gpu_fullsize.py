@@ -1,0 +1,99 @@
+"""Full-size (BASELINE.json configs[3]: 1920x1080, max_dis=256) checks through the C ABI.  The oracle
+needs an 8.5 GB cost volume and ~20 CPU-minutes at this size, so here the result is pinned by
+size-independent properties instead: determinism, per-pixel monotone costs, disparity/plane
+consistency recomputed in numpy, evaluation counters, and ground-truth agreement."""
+import numpy as np
+import pytest
+
+from crossscalepatchmatch_b200.synth import make_pair
+
+pytestmark = pytest.mark.gpu
+
+W, H, D = 1920, 1080, 256
+
+
+@pytest.fixture(scope="module")
+def cspm():
+    import crossscalepatchmatch_b200 as c
+
+    assert c.device_count() > 0
+    return c
+
+
+@pytest.fixture(scope="module")
+def hd(cspm):
+    l, r, gt = make_pair(W, H, D, 0xC5B20003)
+    pc = cspm.PreSSPC(l, r, D, 35, cspm.GetCCType("GRD"))
+    return l, r, gt, pc
+
+
+def _round2int(v):
+    # commfunc.h:117-121: low 32 bits of (v + 1.5*2^52)
+    return (v + 6755399441055744.0).view(np.int64).astype(np.int32)
+
+
+def test_hd_stage_properties(cspm, hd):
+    l, r, gt, pc = hd
+    pm = cspm.CSPatchMatch(l, r, D, 1, seed=0x5EED)
+    pm.stage(cspm.STAGE_INIT, 0, pc)
+    prev = [pm.planes(v)[2].copy() for v in (0, 1)]
+    assert all(np.isfinite(c).all() and (c >= 0).all() for c in prev)
+    for st in (cspm.STAGE_SPATIAL, cspm.STAGE_VIEW, cspm.STAGE_REFINE):
+        pm.stage(st, 0, pc)
+        for v in (0, 1):
+            n, p, c = pm.planes(v)
+            assert (c <= prev[v]).all(), "min_cost must never increase (strict-< acceptance)"
+            assert np.allclose(np.linalg.norm(n, axis=2), 1.0, atol=1e-9)
+            # param is a function of the normal: a = -nx/nz, b = -ny/nz (plane.h:31-32), bit-exact in numpy
+            denom = np.where(n[..., 2] < 0, -np.maximum(np.abs(n[..., 2]), 1e-8), np.maximum(np.abs(n[..., 2]), 1e-8))
+            assert np.array_equal(p[..., 0], -n[..., 0] / denom) and np.array_equal(p[..., 1], -n[..., 1] / denom)
+            prev[v] = c.copy()
+    pm.stage(cspm.STAGE_PLANE2DISP)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    for v in (0, 1):
+        _, p, _ = pm.planes(v)
+        disp = ((0.0 + p[..., 0] * xx) + p[..., 1] * yy) + p[..., 2] * 1.0  # Matx::dot order, no FMA in numpy
+        want = np.clip(_round2int(disp * 1.0), 0, 255).astype(np.uint8)
+        assert np.array_equal(pm.dis(v), want), "PlaneToDisp (cs_patchmatch.cc:590-602)"
+    st = pm.stats()
+    assert st["plane_evals"] == 2 * W * H * (1 + 1 + pm.n_ref()) + 2 * ((W - 1) * H + W * (H - 1))
+
+
+def test_hd_full_run_deterministic_and_accurate(cspm, hd):
+    l, r, gt, pc = hd
+    runs = []
+    for _ in range(2):
+        pm = cspm.CSPatchMatch(l, r, D, 1, seed=0x5EED)
+        pm.PatchMatch(3, pc, False)
+        runs.append((pm.dis(0), pm.dis(1), pm.planes(0)[2]))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2]), "bit-identical costs run to run"
+    # sanity (not parity): agreement with the synthetic ground truth on the left view
+    err = np.abs(runs[0][0].astype(np.float64) - np.minimum(gt, 255.0))
+    frac = (err <= 1.0).mean()
+    assert frac > 0.80, f"only {frac:.3f} of the pixels within +-1 of the ground truth"
+    # a different seed gives a different (but equally good) answer
+    pm = cspm.CSPatchMatch(l, r, D, 1, seed=1234)
+    pm.PatchMatch(3, pc, False)
+    assert not np.array_equal(pm.dis(0), runs[0][0])
+    assert (np.abs(pm.dis(0).astype(np.float64) - np.minimum(gt, 255.0)) <= 1.0).mean() > 0.80
+
+
+def test_hd_shared_plane_cost_and_device_pointer_path(cspm, hd):
+    """One immutable plane cost may serve several CSPatchMatch handles; the device-pointer
+    constructors must give the same result as the host-pointer ones."""
+    import torch
+
+    l, r, gt, pc = hd
+    dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    ptrs = ((dl.data_ptr(), W, H, 3 * W), (dr.data_ptr(), W, H, 3 * W))
+    pc2 = cspm.PreSSPC(None, None, D, 35, cspm.GetCCType("GRD"), device_ptrs=ptrs)
+    a = cspm.CSPatchMatch(l, r, D, 1, seed=9)
+    b = cspm.CSPatchMatch(None, None, D, 1, seed=9, device_ptrs=ptrs)
+    a.stage(cspm.STAGE_INIT, 0, pc)
+    b.stage(cspm.STAGE_INIT, 0, pc2)
+    a.stage(cspm.STAGE_REFINE, 0, pc)
+    b.stage(cspm.STAGE_REFINE, 0, pc2)
+    for v in (0, 1):
+        for x, y in zip(a.planes(v), b.planes(v)):
+            assert np.array_equal(x, y)
