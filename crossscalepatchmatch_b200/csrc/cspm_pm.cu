@@ -545,6 +545,9 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
     CSPM_REQUIRE(l && r, "null image pointer");
     CSPM_REQUIRE(w > 0 && h > 0 && stride >= 3 * w, "bad image geometry");
     CSPM_REQUIRE(max_dis >= 1 && dis_scale >= 1, "max_dis and dis_scale must be >= 1");
+    // ViewPropagation wraps x +- round(d) ONCE (HandleBorder, commfunc.h:129-145); with max_dis > width the
+    // reference indexes past its row arrays (undefined behaviour), so that domain is rejected here.
+    CSPM_REQUIRE(max_dis <= w, "max_dis must not exceed the image width (single wrap-around in ViewPropagation)");
     if (schedule != CSPM_SCHEDULE_RASTER) throw Error(CSPM_EUNSUPPORTED, "only CSPM_SCHEDULE_RASTER is implemented");
     use_device(device);
     cspm_pm* pm = new cspm_pm();

@@ -121,7 +121,9 @@ int cspm_pc_info(const cspm_pc_t* pc, double* scale_wgt, double* max_cost, int* 
 int cspm_pc_scale_image(const cspm_pc_t* pc, int s, int view, uint8_t* out);
 
 /* ---- CSPatchMatch ------------------------------------------------------ */
-/* CSPatchMatch(l_img, r_img, max_dis, dis_scale), cs_patchmatch.cc:3-34 */
+/* CSPatchMatch(l_img, r_img, max_dis, dis_scale), cs_patchmatch.cc:3-34.  Requires 1 <= max_dis <= w:
+ * ViewPropagation wraps x +- round(d) once (HandleBorder, commfunc.h:129-145) and the reference runs
+ * past its row arrays beyond that. */
 cspm_pm_t* cspm_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis,
                           int dis_scale, uint64_t seed, int schedule, int device);
 /* Same, but l/r are DEVICE pointers on `device`. */

@@ -181,9 +181,20 @@ def test_stages_bit_exact(cspm, orc_lib, pair, S, lam):
     (80, 60, 16, 4, 3, 0.3, 2, True),
     (37, 41, 9, 8, 2, 1.0, 2, True),     # odd sizes, window larger than the image at coarse scales
     (130, 20, 40, 1, 0, 0.0, 1, False),  # wide, disparity range ~ image width: heavy wrap-around in view propagation
+    (9, 7, 3, 2, 2, 0.3, 2, True),       # tiny images: every window is clipped on all sides
+    (4, 3, 2, 2, 0, 0.0, 2, True),
+    (1, 5, 1, 1, 0, 0.0, 2, True),       # single column
+    (6, 1, 2, 1, 0, 0.0, 2, False),      # single row
+    (2, 2, 1, 1, 0, 0.0, 1, False),
+    (40, 33, 40, 1, 0, 0.0, 2, True),    # max_dis == width (largest legal range)
 ])
 def test_full_patchmatch_bit_exact(cspm, orc_lib, w, h, d, scale, S, lam, iters, pp):
-    l, r, _ = make_pair(w, h, d, 0xC5B20000 + w)
+    if min(w, h) >= 8 and d >= 4:
+        l, r, _ = make_pair(w, h, d, 0xC5B20000 + w)
+    else:  # degenerate sizes: plain random images
+        rng = np.random.default_rng(w * 100 + h)
+        l = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        r = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
     cc = cspm.GetCCType("GRD")
     po = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam)
     pg = cspm.PreSSPC(l, r, d, 35, cc) if S == 0 else cspm.PreCSPC(l, r, d, 35, S, cc, lam)
@@ -212,6 +223,8 @@ def test_error_behaviour(cspm, pair):
     pg = cspm.PreSSPC(l, r, D, 35, cspm.GetCCType("GRD"))
     with pytest.raises(cspm.CspmError):
         pg.GetPlaneCostBatch([W], [0], [[0, 0, 1.0]], [[0, 0, 1.0]], [0])  # pixel outside the image
+    with pytest.raises(cspm.CspmError):
+        cspm.CSPatchMatch(l[:, :16].copy(), r[:, :16].copy(), 17, 1)  # max_dis > width: UB in the reference, rejected
     small = cspm.CSPatchMatch(l[:32, :32].copy(), r[:32, :32].copy(), D, 4)
     with pytest.raises(cspm.CspmError):
         small.PatchMatch(1, pg)                      # geometry mismatch
