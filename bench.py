@@ -272,6 +272,7 @@ def run_b200(args):
     from crossscalepatchmatch_b200 import shard
 
     units, (t_dev, t_e2e) = shard.aggregate(float(w * h * d * args.steps), [t_dev, t_e2e], device=dev)
+    gpu_launches, _ = shard.aggregate(float(gpu_launches), [0.0], device=dev)  # whole job: summed over ranks
 
     if rank == 0:
         value = units / t_dev / 1e6
