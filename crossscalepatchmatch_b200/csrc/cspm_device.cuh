@@ -42,6 +42,7 @@ struct PcDev {
   double scale_wgt[kMaxScales];
   const double* lut_w;         // [kLutW]
   const double* lut_c;         // [kLutC]
+  const double* lut_rep;       // [766*16 + kLutC]: weight table replicated 16x, then the colour table (bulk kernels)
   double k_grd;                // (1 - ALPHA), evaluated in double on the host
 };
 
@@ -310,12 +311,39 @@ __device__ __forceinline__ void stage_luts(const PcDev& pc, double* s_lut_w, dou
 // reachable entries (L1 distance of two 8-bit BGR pixels <= 765) are staged: 98 KB.
 constexpr int kLutWUsed = 766;
 constexpr int kLutRepShift = 4;
-constexpr size_t kBulkSmemBytes = sizeof(double) * ((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);
-__device__ __forceinline__ void stage_luts_rep(const PcDev& pc, double* s_lut_w_rep, double* s_lut_c) {
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < kLutWUsed * (1 << kLutRepShift); i += nthr) s_lut_w_rep[i] = pc.lut_w[i >> kLutRepShift];
-  for (int i = tid; i < kLutC; i += nthr) s_lut_c[i] = pc.lut_c[i];
+constexpr size_t kBulkLutBytes = sizeof(double) * ((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);  // 98 304 B, multiple of 16
+constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16;  // + the mbarrier
+// The replicated table (+ the colour table right behind it) is prepared once per plane cost in global
+// memory (PcDev::lut_rep) and brought into shared memory by ONE TMA bulk copy (cp.async.bulk, SASS
+// UBLKCP) issued by thread 0 and tracked by an mbarrier; the other threads meanwhile draw their
+// random candidate (Philox) and only wait on the barrier right before the first table lookup.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_stage_luts_begin(const PcDev& pc, double* s_lut, unsigned long long* s_mbar) {
+  const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+  if (leader) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  if (leader) {
+    const uint32_t bytes = (uint32_t)kBulkLutBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(s_mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_lut)),
+                 "l"(pc.lut_rep), "r"(bytes), "r"(smem_u32(s_mbar))
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tma_stage_luts_wait(unsigned long long* s_mbar) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(s_mbar))
+        : "memory");
+  }
 }
 
 // ===========================================================================

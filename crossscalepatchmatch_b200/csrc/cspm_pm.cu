@@ -46,9 +46,10 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 constexpr int kBulkBy = 16;  // bulk kernels: 32 x 16 pixels per CTA, one CTA per SM (98 KB replicated table)
 template <int CC>
 __global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
-  extern __shared__ double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  stage_luts_rep(pc, s_dyn, s_lut_c);
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
   const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
   PlaneD p;
   p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
   update_param(p, (double)x, (double)y, z);
+  tma_stage_luts_wait(s_mbar);
   const double cost = plane_cost<CC, kLutRepShift>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
   store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
 }
@@ -71,9 +73,10 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
 // ----------------------------------------------------------------- refine
 template <int CC>
 __global__ void __launch_bounds__(32 * kBulkBy, 1) k_refine(PcDev pc, PmDev pm, int iter) {
-  extern __shared__ double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  stage_luts_rep(pc, s_dyn, s_lut_c);
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
   const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_refine(PcDev pc, PmDev pm, 
   PlaneD cur = load_plane(pm.st[v], n, i);
   double cur_cost = pm.st[v][6 * n + i];
   double z_iter = ddiv((double)pm.max_dis, 2.0), n_iter = 1.0;  // kMaxNorm_
+  tma_stage_luts_wait(s_mbar);  // tables must have landed before the first lookup
   for (int step = 0; step < pm.n_ref; ++step) {
     const uint64_t stream = stream_refine(pm.h, pm.n_ref, iter, step, v, y);
     const double dz = rng_uniform(pm.seed, stream, 2u * x, 0, -z_iter, z_iter);
@@ -216,9 +220,10 @@ __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, in
 template <int CC>
 __global__ void __launch_bounds__(32 * kBulkBy, 1) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
-  extern __shared__ double s_dyn[];
+  extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  stage_luts_rep(pc, s_dyn, s_lut_c);
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
   const double* s_lut_w = s_dyn + (threadIdx.x & 15);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_view_eval(PcDev pc, PmDev p
     view_candidate(pm, v, x, y, &q, &cor_x);
     // a proposal can only win if it beats the target's cost at the start of this pass
     const double bound = pm.st[v][6 * (size_t)pm.w * pm.h + (size_t)y * pm.w + cor_x];
+    tma_stage_luts_wait(s_mbar);
     const double cost = plane_cost<CC, kLutRepShift>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;

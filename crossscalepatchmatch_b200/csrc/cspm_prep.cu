@@ -358,6 +358,16 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     CSPM_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope below
     D.lut_w = d_lut_w;
     D.lut_c = d_lut_c;
+    {  // 16x replicated weight table + colour table, contiguous, for the bulk kernels' single TMA bulk copy
+      std::vector<double> rep((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);
+      for (int i = 0; i < kLutWUsed; ++i)
+        for (int r = 0; r < (1 << kLutRepShift); ++r) rep[((size_t)i << kLutRepShift) + r] = lut_w[i];
+      for (int k = 0; k < kLutC; ++k) rep[(size_t)kLutWUsed * (1 << kLutRepShift) + k] = lut_c[k];
+      double* d_rep = pc->arena.alloc<double>(rep.size());
+      CSPM_CUDA(cudaMemcpyAsync(d_rep, rep.data(), sizeof(double) * rep.size(), cudaMemcpyHostToDevice, st));
+      CSPM_CUDA(cudaStreamSynchronize(st));
+      D.lut_rep = d_rep;
+    }
 
     // pyramid of dense BGR images (pre_cs_pc.cc:42-49)
     int sw = w, sh = h, sd = max_disp;
