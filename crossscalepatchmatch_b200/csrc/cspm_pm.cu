@@ -468,9 +468,15 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
     int rev_arg = rev;
     unsigned int* bar = pm->grid_barrier;
     void* args[] = {&pcd, &d, &rev_arg, &bar};
-    CSPM_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(sms * kSpCtasPerSm), dim3(kSpThreads), args, smem_p, pm->stream));
-    pm->stats.kernel_launches++;
-  } else {
+    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(sms * kSpCtasPerSm), dim3(kSpThreads), args, smem_p, pm->stream);
+    if (ce == cudaSuccess) {
+      pm->stats.kernel_launches++;
+    } else {  // e.g. SMs partly taken by another context: fall back to one launch per diagonal (same results)
+      cudaGetLastError();
+      persistent = false;
+    }
+  }
+  if (!persistent) {
     const size_t smem = sizeof(double) * (kLutW + kLutC + 2 * (size_t)wnd * wnd);
     for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
       const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
