@@ -46,6 +46,8 @@ SIGNATURES = {
     "cspm_pc_create_cs": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_int]),
     "cspm_pc_create_ss_dev": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "cspm_pc_create_cs_dev": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_int]),
+    "cspm_pc_create_grdpc": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cspm_pc_create_cspc": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
     "cspm_pc_destroy": (None, [C.c_void_p]),
     "cspm_pc_get_plane_cost": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _ip, _dp]),
     "cspm_pc_info": (C.c_int, [C.c_void_p, _dp, _dp, _ip]),

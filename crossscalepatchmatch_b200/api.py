@@ -204,6 +204,32 @@ class PreCSPC(IPlaneCost):
             raise CspmError(_lib.ENODEV, _lib.last_error())
 
 
+class GrdPC(IPlaneCost):
+    """plane_cost/grd_pc.h:19-71 — GrdPC(l_img, r_img, max_disp, wnd_size): image-interpolating plane cost."""
+
+    def __init__(self, l_img, r_img, max_disp, wnd_size, device=0):
+        l, r = _img(l_img), _img(r_img)
+        if l.shape != r.shape or l.strides != r.strides:
+            raise CspmError(_lib.EINVAL, "left/right geometry differs")
+        self._h = dll.cspm_pc_create_grdpc(C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data), l.shape[1], l.shape[0],
+                                           l.strides[0], max_disp, wnd_size, device)
+        if not self._h:
+            raise CspmError(_lib.ENODEV, _lib.last_error())
+
+
+class CSPC(IPlaneCost):
+    """plane_cost/cspc.h:17-62 — CSPC(l_img, r_img, max_disp, wnd_size, scale_num, reg_lambda)."""
+
+    def __init__(self, l_img, r_img, max_disp, wnd_size, scale_num, reg_lambda, device=0):
+        l, r = _img(l_img), _img(r_img)
+        if l.shape != r.shape or l.strides != r.strides:
+            raise CspmError(_lib.EINVAL, "left/right geometry differs")
+        self._h = dll.cspm_pc_create_cspc(C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data), l.shape[1], l.shape[0],
+                                          l.strides[0], max_disp, wnd_size, scale_num, float(reg_lambda), device)
+        if not self._h:
+            raise CspmError(_lib.ENODEV, _lib.last_error())
+
+
 class CSPatchMatch:
     """cs_patchmatch.h:16-147 — CSPatchMatch(l_img, r_img, max_dis, dis_scale)."""
 

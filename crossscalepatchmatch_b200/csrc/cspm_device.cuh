@@ -17,7 +17,9 @@ constexpr int kLutW = 1000;   // exp(-i/10) table, pre_ss_pc.cc:61-64
 constexpr int kLutC = 32;     // colour term table: 0.1*min(k*0.3333333333,10), saturates at k>=31
 constexpr double kDoubleEps = 0.00000001;  // commfunc.h:26
 
-enum CcKind { CC_GRD = 0, CC_CEN = 1 };
+// Raw cost behind the window sum: GrdCC / CenCC volumes (PreSSPC, PreCSPC) or the image-interpolating
+// cost of GrdPC / CSPC (plane_cost/grd_pc.cc, cspc.cc).
+enum CcKind { CC_GRD = 0, CC_CEN = 1, CC_IMG = 2 };
 
 // One pyramid level, both views.  Images are stored padded: `pad` columns on
 // each side hold the reference's out-of-image partner constant
@@ -205,6 +207,29 @@ __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx
   const double q_disp = dadd(dmul(a, (double)qx), q_disp_y);
   const int fl = __double2int_rz(q_disp);  // static_cast<int>: truncation toward zero
   if (fl <= 0 || fl >= t.max_disp) return dmul(wgt, t.max_cost);
+  if (CC == CC_IMG) {
+    // GrdPC / CSPC tap (grd_pc.cc:147-174, cspc.cc:150-175): interpolate the partner IMAGE linearly at the
+    // sub-pixel position q_x -+ d (truncation toward zero, single wrap-around), then TAD colour + gradient.
+    const double other_x = dadd((double)qx, t.raw.dir > 0 ? q_disp : -q_disp);  // q_x + (2*view-1)*q_disp
+    int floor_x = __double2int_rz(other_x);
+    int ceil_x = floor_x + 1;
+    const double floor_wgt = dsub((double)ceil_x, other_x);
+    floor_x = handle_border(floor_x, t.raw.w);
+    ceil_x = handle_border(ceil_x, t.raw.w);
+    const uint32_t If = t.raw.col_o[row_off + floor_x], Ic = t.raw.col_o[row_off + ceil_x];
+    double clr = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int q8 = (Iq >> (8 * c)) & 255, c8 = (Ic >> (8 * c)) & 255, f8 = (If >> (8 * c)) & 255;
+      const double term = fabs(dadd((double)(q8 - c8), dmul(floor_wgt, (double)(c8 - f8))));
+      clr = c == 0 ? term : dadd(clr, term);
+    }
+    clr = dmul(clr, 0.33333333333333);
+    const double Gf = t.raw.grd_o[row_off + floor_x], Gc = t.raw.grd_o[row_off + ceil_x];
+    const double grd = fabs(dadd(dsub(t.grd_v[row_off + qx], Gc), dmul(floor_wgt, dsub(Gc, Gf))));
+    const double val = dadd(dmul(0.1, clr > 10.0 ? 10.0 : clr), dmul(t.raw.k_grd, grd > 2.0 ? 2.0 : grd));
+    return dmul(wgt, val);
+  }
   const double fw = dsub((double)(fl + 1), q_disp);
   const double gq = t.grd_v[row_off + qx];
   const uint32_t qhi = CC == CC_CEN ? t.hi_v[row_off + qx] : 0u;

@@ -87,6 +87,16 @@ struct DeviceArena {
 
 }  // namespace cspm
 
+// Instantiate `body` with `constexpr int CC` bound to the plane cost's raw-cost kind.
+#define CSPM_DISPATCH_CC(kind, ...)                                   \
+  do {                                                                \
+    switch (kind) {                                                   \
+      case ::cspm::CC_CEN: { constexpr int CC = ::cspm::CC_CEN; __VA_ARGS__; } break; \
+      case ::cspm::CC_IMG: { constexpr int CC = ::cspm::CC_IMG; __VA_ARGS__; } break; \
+      default: { constexpr int CC = ::cspm::CC_GRD; __VA_ARGS__; } break;             \
+    }                                                                 \
+  } while (0)
+
 struct cspm_cc {
   int kind;  // cspm::CcKind
   std::string name;

@@ -415,13 +415,7 @@ static void bulk_smem(K kern) {
 
 static void run_init(cspm_pm* pm, const cspm_pc* pc) {
   dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  if (pc->dev.cc_kind == CC_CEN) {
-    bulk_smem(k_init<CC_CEN>);
-    k_init<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm));
-  } else {
-    bulk_smem(k_init<CC_GRD>);
-    k_init<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm));
-  }
+  CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_init<CC>); k_init<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm)));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
@@ -429,13 +423,7 @@ static void run_init(cspm_pm* pm, const cspm_pc* pc) {
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
   dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  if (pc->dev.cc_kind == CC_CEN) {
-    bulk_smem(k_refine<CC_CEN>);
-    k_refine<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter);
-  } else {
-    bulk_smem(k_refine<CC_GRD>);
-    k_refine<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter);
-  }
+  CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_refine<CC>); k_refine<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
@@ -453,8 +441,8 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   bool persistent = !force_diag;
   const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
   int sms = 0, coop = 0, occ = 0;
-  auto kern = pcd.cc_kind == CC_CEN ? (wnd == 35 ? k_spatial_persist<CC_CEN, 35> : k_spatial_persist<CC_CEN, 0>)
-                                    : (wnd == 35 ? k_spatial_persist<CC_GRD, 35> : k_spatial_persist<CC_GRD, 0>);
+  void (*kern)(PcDev, PmDev, int, unsigned int*) = nullptr;
+  CSPM_DISPATCH_CC(pcd.cc_kind, kern = wnd == 35 ? k_spatial_persist<CC, 35> : k_spatial_persist<CC, 0>);
   if (persistent) {
     CSPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pm->device));
     CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm->device));
@@ -481,8 +469,7 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
     for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
       const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
       dim3 g(u_hi - u_lo + 1, 2);
-      if (pcd.cc_kind == CC_CEN) k_spatial_diag<CC_CEN><<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
-      else k_spatial_diag<CC_GRD><<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev);
+      CSPM_DISPATCH_CC(pcd.cc_kind, k_spatial_diag<CC><<<g, 128, smem, pm->stream>>>(pcd, d, diag, u_lo, rev));
       pm->stats.kernel_launches++;
     }
   }
@@ -500,13 +487,8 @@ static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
   for (int v = 0; v < 2; ++v) {
     k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
     dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy);
-    if (pc->dev.cc_kind == CC_CEN) {
-      bulk_smem(k_view_eval<CC_CEN>);
-      k_view_eval<CC_CEN><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
-    } else {
-      bulk_smem(k_view_eval<CC_GRD>);
-      k_view_eval<CC_GRD><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter);
-    }
+    CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_view_eval<CC>);
+                     k_view_eval<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter));
     dim3 g1((pm->w + 127) / 128, pm->h);
     k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
     k_view_commit<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->win);

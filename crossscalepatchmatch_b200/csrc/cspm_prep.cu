@@ -79,6 +79,26 @@ __global__ void k_pack(const uint8_t* __restrict__ bgr, int w, int h, int pad, i
   grad[o] = g;
 }
 
+// K1a': the same for GrdPC / CSPC (grd_pc.cc:37-40): cvtColor(BGR2GRAY) on 8 bits (14-bit fixed point)
+// then Sobel(ksize=1) -> integer-valued f64 gradient.  Partner reads wrap around, so the pad is unused.
+__device__ __forceinline__ int gray8_of_bgr8(const uint8_t* p) { return (p[2] * 4899 + p[1] * 9617 + p[0] * 1868 + 8192) >> 14; }
+__global__ void k_pack_img(const uint8_t* __restrict__ bgr, int w, int h, int pad, int pitch,
+                           uint32_t* __restrict__ color, double* __restrict__ grad) {
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (xp >= pitch) return;
+  const int x = xp - pad;
+  const size_t o = (size_t)y * pitch + xp;
+  if (x < 0 || x >= w) {
+    color[o] = 0u;
+    grad[o] = 0.0;
+    return;
+  }
+  const uint8_t* p = bgr + ((size_t)y * w + x) * 3;
+  color[o] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+  grad[o] = (x > 0 && x < w - 1) ? (double)(gray8_of_bgr8(p + 3) - gray8_of_bgr8(p - 3)) : 0.0;
+}
+
 // K1b: pyrDown on CV_8UC3 — separable [1 4 6 4 1], REFLECT_101, (sum+128)>>8.
 __device__ __forceinline__ int reflect101(int p, int n) {
   if (n == 1) return 0;
@@ -325,6 +345,9 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
   CSPM_REQUIRE(max_disp >= 1, "max_disp must be >= 1");
   CSPM_REQUIRE(wnd_size >= 1 && wnd_size <= 63, "wnd_size out of range [1,63]");
   CSPM_REQUIRE(!cross_scale || (scale_num >= 2 && scale_num <= kMaxScales), "scale_num out of range [2,8]");
+  // GrdPC / CSPC wrap the interpolated partner column once (HandleBorder): beyond max_disp <= width the reference
+  // reads outside its rows
+  CSPM_REQUIRE(cc->kind != CC_IMG || max_disp <= w, "GrdPC/CSPC need max_disp <= image width");
   use_device(device);
 
   cspm_pc* pc = new cspm_pc();
@@ -396,7 +419,8 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
         uint32_t* color = pc->arena.alloc<uint32_t>((size_t)S.pitch * sh);
         double* grad = pc->arena.alloc<double>((size_t)S.pitch * sh);
         dim3 g((S.pitch + 127) / 128, sh);
-        k_pack<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad);
+        if (cc->kind == CC_IMG) k_pack_img<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad);
+        else k_pack<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad);
         pc->stats.kernel_launches++;
         S.color[v] = color;
         S.grad[v] = grad;
@@ -418,7 +442,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     // raw-cost maxima (pre_ss_pc.cc:51-58 / pre_cs_pc.cc:75-82)
     unsigned long long* d_max = pc->arena.alloc<unsigned long long>(2 * kMaxScales);
     CSPM_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * 2 * kMaxScales, st));
-    for (int s = 0; s < pc->scale_num; ++s)
+    for (int s = 0; s < pc->scale_num && cc->kind != CC_IMG; ++s)
       for (int v = 0; v < 2; ++v) {
         dim3 g((D.sc[s].w + 127) / 128, D.sc[s].h);
         if (cc->kind == CC_CEN) k_max_raw_cost<CC_CEN><<<g, 128, 0, st>>>(D, s, v, d_max + v * kMaxScales + s);
@@ -433,6 +457,8 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
       for (int v = 0; v < 2; ++v) {
         double m;
         std::memcpy(&m, &h_max[v * kMaxScales + s], 8);
+        // GrdPC / CSPC charge an impossible disparity COST_ALPHA*TAU_CLR + (1-COST_ALPHA)*TAU_GRD (grd_pc.cc:114-116)
+        if (cc->kind == CC_IMG) m = 0.1 * 10.0 + (1 - 0.1) * 2.0;
         pc->max_cost[v][s] = m;
         D.sc[s].max_cost[v] = m;
       }
@@ -577,6 +603,16 @@ cspm_pc_t* cspm_pc_create_cs_dev(const uint8_t* l, const uint8_t* r, int w, int 
                                  int wnd_size, int scale_num, const cspm_cc_t* cc, double reg_lambda, int device) {
   return guard_ptr<cspm_pc>([&] { return pc_create(l, r, true, w, h, stride, max_disp, wnd_size, scale_num, true, cc, reg_lambda, device); });
 }
+cspm_pc_t* cspm_pc_create_grdpc(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_disp, int wnd_size,
+                                int device) {
+  const cspm_cc img{CC_IMG, "IMG"};
+  return guard_ptr<cspm_pc>([&] { return pc_create(l, r, false, w, h, stride, max_disp, wnd_size, 1, false, &img, 0.0, device); });
+}
+cspm_pc_t* cspm_pc_create_cspc(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_disp, int wnd_size,
+                               int scale_num, double reg_lambda, int device) {
+  const cspm_cc img{CC_IMG, "IMG"};
+  return guard_ptr<cspm_pc>([&] { return pc_create(l, r, false, w, h, stride, max_disp, wnd_size, scale_num, true, &img, reg_lambda, device); });
+}
 void cspm_pc_destroy(cspm_pc_t* pc) {
   if (!pc) return;
   cudaSetDevice(pc->device);
@@ -612,8 +648,7 @@ int cspm_pc_get_plane_cost(const cspm_pc_t* pc, int n, const int* x, const int* 
       CSPM_CUDA(cudaMemcpyAsync(d_v, view, sizeof(int) * n, cudaMemcpyHostToDevice, st));
       CSPM_CUDA(cudaMemcpyAsync(d_n, normal_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
       CSPM_CUDA(cudaMemcpyAsync(d_p, point_xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
-      if (pc->dev.cc_kind == CC_CEN) k_plane_cost_batch<CC_CEN><<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o);
-      else k_plane_cost_batch<CC_GRD><<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o);
+      CSPM_DISPATCH_CC(pc->dev.cc_kind, k_plane_cost_batch<CC><<<(n + 127) / 128, 128, 0, st>>>(pc->dev, n, d_x, d_y, d_n, d_p, d_v, d_o));
       CSPM_CUDA(cudaGetLastError());
       pc->stats.kernel_launches++;
       pc->stats.plane_evals += n;

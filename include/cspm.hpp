@@ -173,6 +173,25 @@ class PreCSPC : public IPlaneCost {  // plane_cost/pre_cs_pc.h:19-62
   }
 };
 
+class GrdPC : public IPlaneCost {  // plane_cost/grd_pc.h:19-71
+ public:
+  GrdPC(const Mat& l_img, const Mat& r_img, const int& max_disp, const int& wnd_size, int device = 0) {
+    require_8uc3(l_img, r_img);
+    h_ = cspm_pc_create_grdpc(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size, device);
+    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+  }
+};
+class CSPC : public IPlaneCost {  // plane_cost/cspc.h:17-62
+ public:
+  CSPC(const Mat& l_img, const Mat& r_img, const int& max_disp, const int& wnd_size, const int& scale_num,
+       const double& reg_lambda, int device = 0) {
+    require_8uc3(l_img, r_img);
+    h_ = cspm_pc_create_cspc(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size,
+                             scale_num, reg_lambda, device);
+    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+  }
+};
+
 // cs_patchmatch.h:16-147
 class CSPatchMatch {
  public:

@@ -105,6 +105,14 @@ cspm_pc_t* cspm_pc_create_ss_dev(const uint8_t* d_l, const uint8_t* d_r, int w, 
 cspm_pc_t* cspm_pc_create_cs_dev(const uint8_t* d_l, const uint8_t* d_r, int w, int h, int stride,
                                  int max_disp, int wnd_size, int scale_num, const cspm_cc_t* cc,
                                  double reg_lambda, int device);
+/* GrdPC(l_img, r_img, max_disp, wnd_size), plane_cost/grd_pc.cc:12-66, and
+ * CSPC(l_img, r_img, max_disp, wnd_size, scale_num, reg_lambda), plane_cost/cspc.cc:3-92: the
+ * alternative IPlaneCost plugins that interpolate the partner IMAGE at the sub-pixel position instead of
+ * reading a cost volume (no CCMethod involved).  Require max_disp <= w (single wrap-around). */
+cspm_pc_t* cspm_pc_create_grdpc(const uint8_t* l, const uint8_t* r, int w, int h, int stride,
+                                int max_disp, int wnd_size, int device);
+cspm_pc_t* cspm_pc_create_cspc(const uint8_t* l, const uint8_t* r, int w, int h, int stride,
+                               int max_disp, int wnd_size, int scale_num, double reg_lambda, int device);
 void cspm_pc_destroy(cspm_pc_t* pc);
 /* Batched IPlaneCost::GetPlaneCost(ref_x, ref_y, plane, view)
  * (pre_ss_pc.cc:74-118 / pre_cs_pc.cc:133-188): query i is the plane with

@@ -60,6 +60,7 @@ inline uint64_t cspm_shim_time() {
 #define CV_BGR2RGB 4
 #define CV_BGR2GRAY 6
 #define CV_RGB2GRAY 7
+#define CV_BGR2Lab 44
 #define CV_Assert(expr)                                                          \
   do {                                                                           \
     if (!(expr)) throw std::runtime_error(std::string("CV_Assert failed: ") + #expr); \
@@ -229,15 +230,27 @@ static inline void cvtColor(const Mat& src, Mat& dst, int code) {
       const uchar* s = src.ptr<uchar>(y);
       uchar* d = out.ptr<uchar>(y);
       for (int x = 0; x < src.cols; ++x)
-        d[x] = (uchar)((s[3 * x + ri] * 4899 + s[3 * x + 1] * 9617 + s[3 * x + bi] * 1868 + 8192) >> 14);
+        d[x] = cspm_prims::gray8_fixed(s[3 * x + ri], s[3 * x + 1], s[3 * x + bi]);
     }
     dst = out;
+  } else if (code == CV_BGR2Lab) {
+    // grd_pc.cc:32 / cspc.cc:41 compute lab_ but never read it (USE_LAB_WGT is off): any image will do.
+    dst = src.clone();
   } else {
     throw std::runtime_error("cvshim: unsupported cvtColor code");
   }
 }
 
 static inline void Sobel(const Mat& src, Mat& dst, int ddepth, int dx, int dy, int ksize) {
+  if (src.type() == CV_8UC1) {  // grd_pc.cc:40, cspc.cc:47
+    CV_Assert(ddepth == CV_64F && dx == 1 && dy == 0 && ksize == 1);
+    std::vector<uchar> g8((size_t)src.rows * src.cols);
+    for (int y = 0; y < src.rows; ++y) std::memcpy(&g8[(size_t)y * src.cols], src.ptr<uchar>(y), src.cols);
+    Mat out8(src.rows, src.cols, CV_64FC1);
+    cspm_prims::sobel_x_k1_u8(g8.data(), src.cols, src.rows, out8.ptr<double>(0));
+    dst = out8;
+    return;
+  }
   CV_Assert(src.type() == CV_32FC1 && ddepth == CV_64F && dx == 1 && dy == 0 && ksize == 1);
   std::vector<float> g((size_t)src.rows * src.cols);
   for (int y = 0; y < src.rows; ++y) std::memcpy(&g[(size_t)y * src.cols], src.ptr<float>(y), sizeof(float) * src.cols);

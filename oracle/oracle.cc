@@ -7,6 +7,8 @@
 //   CSPM/cc/cen_cc.cc:4-138                 CenCC raw cost (census)
 //   CSPM/plane_cost/pre_ss_pc.cc:12-118     PreSSPC ctor + GetPlaneCost
 //   CSPM/plane_cost/pre_cs_pc.cc:12-188     PreCSPC ctor + GetPlaneCost
+//   CSPM/plane_cost/grd_pc.cc:12-178        GrdPC  (image-interpolating plane cost, single scale)
+//   CSPM/plane_cost/cspc.cc:3-182           CSPC   (the same over a pyramid)
 //   CSPM/cs_patchmatch.cc:3-34,51-345,590-602  CSPatchMatch driver
 //   CSPM/cs_patchmatch.cc:347-588           post-processing (use_pp)
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
@@ -427,6 +429,130 @@ struct PreCSPC : IPlaneCost {  // plane_cost/pre_cs_pc.cc
   }
 };
 
+// GrdPC (grd_pc.cc) and CSPC (cspc.cc): the raw cost is computed on the fly by linearly
+// interpolating the partner IMAGE (colour and 8-bit-gray x-gradient) at the sub-pixel position
+// q_x -+ d, with wrap-around (HandleBorder); scale_num == 0 -> GrdPC, else CSPC.
+const double COST_ALPHA = 0.1;  // grd_pc.h:13-16
+struct ImgPC : IPlaneCost {
+  struct Level {
+    int w, h, max_disp;
+    Img8 img[kViewNum];
+    std::vector<double> grd[kViewNum];
+  };
+  int wnd_size, scale_num;  // scale_num == 0: GrdPC
+  std::vector<Level> lv;
+  std::vector<double> scale_wgt, lookup_exp;
+  ImgPC(const Img8& l, const Img8& r, int max_disp, int wnd, int scale_num_, double reg_lambda)
+      : wnd_size(wnd), scale_num(scale_num_) {
+    const int S = std::max(scale_num, 1);
+    lv.resize(S);
+    lv[0].img[kLeft] = l; lv[0].img[kRight] = r;
+    lv[0].w = l.w; lv[0].h = l.h; lv[0].max_disp = max_disp;
+    for (int s = 0; s < S; ++s) {
+      if (s > 0) {  // cspc.cc:33-38
+        lv[s].h = (lv[s - 1].h + 1) / 2;
+        lv[s].w = (lv[s - 1].w + 1) / 2;
+        lv[s].max_disp = lv[s - 1].max_disp / 2;
+      }
+      for (int v = 0; v < kViewNum; ++v) {
+        Img8& d = lv[s].img[v];
+        if (s > 0) {
+          d.w = lv[s].w; d.h = lv[s].h; d.d.resize((size_t)d.w * d.h * 3);
+          const Img8& p = lv[s - 1].img[v];
+          pyrdown_u8c3(p.d.data(), p.w, p.h, 3 * p.w, d.d.data(), d.w, d.h, 3 * d.w);
+        }
+        // cvtColor(BGR2GRAY) 8U + Sobel(64F,1,0,1)  (grd_pc.cc:37-40, cspc.cc:44-47)
+        std::vector<uint8_t> gray((size_t)d.w * d.h);
+        for (size_t i = 0; i < gray.size(); ++i) gray[i] = gray8_fixed(d.d[3 * i + 2], d.d[3 * i + 1], d.d[3 * i]);
+        lv[s].grd[v].assign(gray.size(), 0.0);
+        sobel_x_k1_u8(gray.data(), d.w, d.h, lv[s].grd[v].data());
+      }
+    }
+    if (scale_num > 0) {  // cspc.cc:51-72
+      std::vector<double> reg((size_t)S * S, 0.0), inv((size_t)S * S, 0.0);
+      auto at = [&](int r_, int c_) -> double& { return reg[(size_t)r_ * S + c_]; };
+      for (int s = 0; s < S; ++s) {
+        if (s == 0) { at(s, s) = 1 + reg_lambda; at(s, s + 1) = -reg_lambda; }
+        else if (s == S - 1) { at(s, s) = 1 + reg_lambda; at(s, s - 1) = -reg_lambda; }
+        else { at(s, s) = 1 + 2 * reg_lambda; at(s, s - 1) = -reg_lambda; at(s, s + 1) = -reg_lambda; }
+      }
+      invert_lu(reg.data(), S, inv.data());
+      scale_wgt.assign(inv.begin(), inv.begin() + S);
+    } else {
+      scale_wgt.assign(1, 1.0);
+    }
+    make_exp_lut(&lookup_exp);
+  }
+  // grd_pc.cc:84-176 == cspc.cc:122-175
+  double window(const Level& L, int ref_x, int ref_y, double plane_a, double plane_b, double plane_c, int view) const {
+    const int half_wnd = wnd_size / 2;
+    double cost = 0.0;
+    const uint8_t* I_p = L.img[view].row(ref_y) + 3 * ref_x;
+    for (int dy = -half_wnd; dy <= half_wnd; ++dy) {
+      int q_y = ref_y + dy;
+      if (q_y >= 0 && q_y < L.h) {
+        const uint8_t* I_q_y = L.img[view].row(q_y);
+        const double* G_q_y = L.grd[view].data() + (size_t)q_y * L.w;
+        const uint8_t* I_ohter_y = L.img[1 - view].row(q_y);
+        const double* G_other_y = L.grd[1 - view].data() + (size_t)q_y * L.w;
+        const double q_disp_y = plane_b * q_y + plane_c;
+        for (int dx = -half_wnd; dx <= half_wnd; ++dx) {
+          int q_x = ref_x + dx;
+          if (q_x >= 0 && q_x < L.w) {
+            const uint8_t* I_q = I_q_y + 3 * q_x;
+            int sum = std::abs(I_p[0] - I_q[0]) + std::abs(I_p[1] - I_q[1]) + std::abs(I_p[2] - I_q[2]);
+            const double wgt = lookup_exp[sum];
+            double q_disp = plane_a * q_x + q_disp_y;
+            int q_disp_floor;
+            if (!(q_disp > -2147483649.0 && q_disp < 2147483648.0)) q_disp_floor = INT32_MIN;
+            else q_disp_floor = static_cast<int>(q_disp);
+            if (q_disp_floor <= 0 || q_disp_floor >= L.max_disp) {
+              cost += wgt * (COST_ALPHA * TAU_CLR + (1 - COST_ALPHA) * TAU_GRD);
+            } else {
+              const double other_x = q_x + (2 * view - 1) * q_disp;
+              int floor_x = static_cast<int>(other_x);
+              int ceil_x = floor_x + 1;
+              const double floor_wgt = ceil_x - other_x;
+              floor_x = HandleBorder(floor_x, L.w);
+              ceil_x = HandleBorder(ceil_x, L.w);
+              const uint8_t* I_floor = I_ohter_y + 3 * floor_x;
+              const uint8_t* I_ceil = I_ohter_y + 3 * ceil_x;
+              double clr_cost = std::fabs(I_q[0] - I_ceil[0] + floor_wgt * (I_ceil[0] - I_floor[0])) +
+                                std::fabs(I_q[1] - I_ceil[1] + floor_wgt * (I_ceil[1] - I_floor[1])) +
+                                std::fabs(I_q[2] - I_ceil[2] + floor_wgt * (I_ceil[2] - I_floor[2]));
+              clr_cost *= 0.33333333333333;
+              const double G_floor = G_other_y[floor_x];
+              const double G_ceil = G_other_y[ceil_x];
+              double grd_cost = std::fabs(G_q_y[q_x] - G_ceil + floor_wgt * (G_ceil - G_floor));
+              cost += wgt * (COST_ALPHA * std::min(clr_cost, TAU_CLR) + (1 - COST_ALPHA) * std::min(grd_cost, TAU_GRD));
+            }
+          }
+        }
+      }
+    }
+    return cost;
+  }
+  double GetPlaneCost(int ref_x, int ref_y, const Plane& plane, RefView view) const override {
+    if (scale_num == 0)  // GrdPC::GetPlaneCost, grd_pc.cc:71-178
+      return window(lv[0], ref_x, ref_y, plane.param[0], plane.param[1], plane.param[2], view);
+    double cost = 0.0;   // CSPC::GetPlaneCost, cspc.cc:107-182
+    double cur_disp = plane.param[0] * ref_x + plane.param[1] * ref_y + plane.param[2];
+    int cur_y = ref_y, cur_x = ref_x;
+    for (int s = 0; s < scale_num; ++s) {
+      Plane cur_plane;
+      cur_plane.set_norm(plane.norm[0], plane.norm[1], plane.norm[2]);
+      cur_plane.set_point(cur_x, cur_y, cur_disp);
+      cur_plane.update_param();
+      double scale_cost = window(lv[s], cur_x, cur_y, cur_plane.param[0], cur_plane.param[1], cur_plane.param[2], view);
+      cost += scale_cost * scale_wgt[s];
+      cur_y /= 2;
+      cur_x /= 2;
+      cur_disp /= 2.0;
+    }
+    return cost;
+  }
+};
+
 // -------------------------------------------------------------- CSPatchMatch
 const double WMF_GAMMA = 10.0;  // cs_patchmatch.h:14
 
@@ -786,6 +912,8 @@ int orc_cc_build_cv(const char* name, const double* l_rgb, const double* r_rgb, 
 // IPlaneCost (scale_num == 0 -> PreSSPC, else PreCSPC)
 void* orc_pc_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_disp,
                     int wnd_size, int scale_num, double reg_lambda, const char* cc_name) {
+  if (std::string(cc_name) == "IMG")  // GrdPC (scale_num == 0) / CSPC: no CCMethod involved
+    return (IPlaneCost*)new ImgPC(load_img(l, w, h, stride), load_img(r, w, h, stride), max_disp, wnd_size, scale_num, reg_lambda);
   CCMethod* cc = GetCCType(cc_name);
   if (!cc) return nullptr;
   Img8 li = load_img(l, w, h, stride), ri = load_img(r, w, h, stride);
@@ -818,6 +946,15 @@ int orc_pc_info(const void* pc, double* scale_wgt, double* max_cost, int* dims) 
     if (dims) { dims[0] = ss->s0.w; dims[1] = ss->s0.h; dims[2] = ss->s0.max_disp; }
     return 1;
   }
+  if (auto ip = dynamic_cast<const ImgPC*>(p)) {
+    const int S = (int)ip->lv.size();
+    for (int s = 0; s < S; ++s) {
+      if (scale_wgt) scale_wgt[s] = ip->scale_wgt[s];
+      if (max_cost) { max_cost[s] = 2.8; max_cost[S + s] = 2.8; }
+      if (dims) { dims[3 * s] = ip->lv[s].w; dims[3 * s + 1] = ip->lv[s].h; dims[3 * s + 2] = ip->lv[s].max_disp; }
+    }
+    return S;
+  }
   auto cs = dynamic_cast<const PreCSPC*>(p);
   int S = cs->scale_num;
   for (int s = 0; s < S; ++s) {
@@ -832,6 +969,7 @@ int orc_pc_scale_image(const void* pc, int s, int view, uint8_t* out) {
   const IPlaneCost* p = (const IPlaneCost*)pc;
   const Img8* im = nullptr;
   if (auto ss = dynamic_cast<const PreSSPC*>(p)) im = &ss->s0.img[view];
+  else if (auto ip = dynamic_cast<const ImgPC*>(p)) im = &ip->lv[s].img[view];
   else im = &dynamic_cast<const PreCSPC*>(p)->sc[s].img[view];
   std::memcpy(out, im->d.data(), im->d.size());
   return 0;

@@ -14,6 +14,8 @@
 #include "cs_patchmatch.h"
 #include "plane_cost/pre_ss_pc.h"
 #include "plane_cost/pre_cs_pc.h"
+#include "plane_cost/grd_pc.h"
+#include "plane_cost/cspc.h"
 #include "cc/grd_cc.h"
 #include "cc/cen_cc.h"
 #undef private
@@ -76,15 +78,25 @@ struct RefPC {
   IPlaneCost* pc;
   PreSSPC* ss;
   PreCSPC* cs;
+  GrdPC* gp;
+  CSPC* cp;
 };
 
 void* ref_pc_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_disp,
                     int wnd_size, int scale_num, double reg_lambda, const char* cc_name) {
+  if (std::string(cc_name) == "IMG") {  // GrdPC / CSPC take no CCMethod (grd_pc.h:20-22, cspc.h:21-23)
+    Quiet q;
+    Mat lm(h, w, CV_8UC3, (void*)l, (size_t)stride), rm(h, w, CV_8UC3, (void*)r, (size_t)stride);
+    RefPC* p = new RefPC{NULL, NULL, NULL, NULL, NULL};
+    if (scale_num == 0) p->pc = p->gp = new GrdPC(lm, rm, max_disp, wnd_size);
+    else p->pc = p->cp = new CSPC(lm, rm, max_disp, wnd_size, scale_num, reg_lambda);
+    return p;
+  }
   CCMethod* cc = get_cc(cc_name);
   if (!cc) return NULL;
   Quiet q;
   Mat lm(h, w, CV_8UC3, (void*)l, (size_t)stride), rm(h, w, CV_8UC3, (void*)r, (size_t)stride);
-  RefPC* p = new RefPC{NULL, NULL, NULL};
+  RefPC* p = new RefPC{NULL, NULL, NULL, NULL, NULL};
   if (scale_num == 0) p->pc = p->ss = new PreSSPC(lm, rm, max_disp, wnd_size, cc);
   else p->pc = p->cs = new PreCSPC(lm, rm, max_disp, wnd_size, scale_num, cc, reg_lambda);
   delete cc;
@@ -114,6 +126,21 @@ int ref_pc_info(const void* p_, double* scale_wgt, double* max_cost, int* dims) 
     if (dims) { dims[0] = p->ss->wid_; dims[1] = p->ss->hei_; dims[2] = p->ss->max_disp_; }
     return 1;
   }
+  if (p->gp) {
+    if (scale_wgt) scale_wgt[0] = 1.0;
+    if (max_cost) { max_cost[0] = 2.8; max_cost[1] = 2.8; }
+    if (dims) { dims[0] = p->gp->wid_; dims[1] = p->gp->hei_; dims[2] = p->gp->max_disp_; }
+    return 1;
+  }
+  if (p->cp) {
+    int S = p->cp->scale_num_;
+    for (int s = 0; s < S; ++s) {
+      if (scale_wgt) scale_wgt[s] = p->cp->scale_wgt_[s];
+      if (max_cost) { max_cost[s] = 2.8; max_cost[S + s] = 2.8; }
+      if (dims) { dims[3 * s] = p->cp->wid_[s]; dims[3 * s + 1] = p->cp->hei_[s]; dims[3 * s + 2] = p->cp->max_disp_[s]; }
+    }
+    return S;
+  }
   int S = p->cs->scale_num_;
   for (int s = 0; s < S; ++s) {
     if (scale_wgt) scale_wgt[s] = p->cs->scale_wgt_[s];
@@ -124,7 +151,7 @@ int ref_pc_info(const void* p_, double* scale_wgt, double* max_cost, int* dims) 
 }
 int ref_pc_scale_image(const void* p_, int s, int view, uint8_t* out) {
   const RefPC* p = (const RefPC*)p_;
-  const Mat& m = p->ss ? p->ss->img_[view] : p->cs->img_[view][s];
+  const Mat& m = p->ss ? p->ss->img_[view] : p->gp ? p->gp->img_[view] : p->cp ? p->cp->img_[view][s] : p->cs->img_[view][s];
   for (int y = 0; y < m.rows; ++y) memcpy(out + (size_t)y * 3 * m.cols, m.ptr<uchar>(y), (size_t)3 * m.cols);
   return 0;
 }

@@ -33,8 +33,9 @@ nm[:20] = [0, 0, 1]
 pt = np.stack([x, y, rng.uniform(-1, d + 1, n)], 1).astype(np.float64)
 pt[:20, 2] = rng.integers(1, d, 20)
 out["q_x"], out["q_y"], out["q_v"], out["q_n"], out["q_p"] = x, y, v, nm, pt
-for tag, S, lam in (("ss", 0, 0.0), ("cs3", 3, 0.3), ("cs5", 5, 0.3)):
-    pc = orc.PlaneCost(R, l, r, d, 35, S, lam)
+for tag, S, lam, cc in (("ss", 0, 0.0, "GRD"), ("cs3", 3, 0.3, "GRD"), ("cs5", 5, 0.3, "GRD"),
+                        ("cen", 0, 0.0, "CEN"), ("grdpc", 0, 0.0, "IMG"), ("cspc3", 3, 0.3, "IMG")):
+    pc = orc.PlaneCost(R, l, r, d, 35, S, lam, cc_name=cc)
     wgt, mc, dims = pc.info()
     out[f"{tag}_wgt"], out[f"{tag}_maxcost"], out[f"{tag}_dims"] = wgt, mc, dims
     out[f"{tag}_cost"] = pc.get_plane_cost(x, y, nm, pt, v, 1)

@@ -122,6 +122,29 @@ def test_census_plane_cost_and_patchmatch(cspm, orc_lib, pair, S, lam):
         assert np.array_equal(mo.dis(view), mg.dis(view))
 
 
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (3, 0.3)])
+def test_image_interpolating_plane_costs(cspm, orc_lib, pair, S, lam):
+    """GrdPC (plane_cost/grd_pc.cc) and CSPC (plane_cost/cspc.cc): the alternative IPlaneCost plugins."""
+    l, r = pair
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam, cc_name="IMG")
+    pg = cspm.GrdPC(l, r, D, 35) if S == 0 else cspm.CSPC(l, r, D, 35, S, lam)
+    for a, b in zip(po.info(), pg.info()):
+        assert np.array_equal(a, b)
+    x, y, nm, pt, v = _queries(np.random.default_rng(4), W, H, D, 3000)
+    co, cg = po.get_plane_cost(x, y, nm, pt, v), pg.GetPlaneCostBatch(x, y, nm, pt, v)
+    bad = np.flatnonzero(co != cg)
+    assert bad.size == 0, f"{bad.size} costs differ, first {bad[:5]}: {co[bad[:5]]} vs {cg[bad[:5]]}"
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=33)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=33)
+    mo.patchmatch(2, po, True)
+    mg.PatchMatch(2, pg, True)
+    _same_state(mo, mg, "GrdPC/CSPC full run")
+    for view in (0, 1):
+        assert np.array_equal(mo.dis(view), mg.dis(view))
+    with pytest.raises(cspm.CspmError):
+        cspm.GrdPC(l[:, :16].copy(), r[:, :16].copy(), 17, 35)  # max_disp > width: out-of-row reads in the reference
+
+
 @pytest.mark.parametrize("wnd", [5, 11, 21, 41])
 def test_other_window_sizes(cspm, orc_lib, wnd):
     """wnd_size is a constructor argument of PreSSPC/PreCSPC (main.cc fixes 35): the generic-window

@@ -10,7 +10,9 @@ import pytest
 import orc
 
 V = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
-TAGS = (("ss", 0, 0.0), ("cs3", 3, 0.3), ("cs5", 5, 0.3))
+TAGS = (("ss", 0, 0.0, "GRD"), ("cs3", 3, 0.3, "GRD"), ("cs5", 5, 0.3, "GRD"),
+        ("cen", 0, 0.0, "CEN"),                                # PreSSPC over CenCC
+        ("grdpc", 0, 0.0, "IMG"), ("cspc3", 3, 0.3, "IMG"))   # GrdPC, CSPC
 
 
 def test_cost_volume_vs_golden(orc_lib):
@@ -23,11 +25,11 @@ def test_cost_volume_vs_golden(orc_lib):
     assert np.array_equal(orc_lib.build_cv("CEN", lrgb, rrgb, d + 1, 1), V["cen_right"])
 
 
-@pytest.mark.parametrize("tag,S,lam", TAGS)
-def test_plane_cost_and_patchmatch_vs_golden(orc_lib, tag, S, lam):
+@pytest.mark.parametrize("tag,S,lam,cc", TAGS)
+def test_plane_cost_and_patchmatch_vs_golden(orc_lib, tag, S, lam, cc):
     l, r = V["l"], V["r"]
     d = int(V["whd"][2])
-    pc = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam)
+    pc = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam, cc_name=cc)
     wgt, mc, dims = pc.info()
     assert np.array_equal(wgt, V[f"{tag}_wgt"]) and np.array_equal(mc, V[f"{tag}_maxcost"]) and np.array_equal(dims, V[f"{tag}_dims"])
     cost = pc.get_plane_cost(V["q_x"], V["q_y"], V["q_n"], V["q_p"], V["q_v"])
@@ -45,13 +47,15 @@ def test_plane_cost_and_patchmatch_vs_golden(orc_lib, tag, S, lam):
         assert np.array_equal(pm.dis(view), V[f"{tag}_dispp{view}"])
 
 
-@pytest.mark.parametrize("w,h,d,S,lam,iters", [(40, 30, 10, 0, 0.0, 3), (33, 27, 20, 3, 0.5, 2), (70, 12, 30, 2, 0.3, 1)])
-def test_live_against_reference_build(orc_lib, ref_lib, w, h, d, S, lam, iters):
+@pytest.mark.parametrize("w,h,d,S,lam,iters,cc", [(40, 30, 10, 0, 0.0, 3, "GRD"), (33, 27, 20, 3, 0.5, 2, "GRD"),
+                                                  (70, 12, 30, 2, 0.3, 1, "GRD"), (36, 28, 9, 3, 0.3, 2, "CEN"),
+                                                  (40, 30, 10, 0, 0.0, 2, "IMG"), (33, 27, 20, 3, 0.5, 2, "IMG")])
+def test_live_against_reference_build(orc_lib, ref_lib, w, h, d, S, lam, iters, cc):
     from crossscalepatchmatch_b200.synth import make_pair
 
     ref_lib.set_time_mode(0)
     l, r, _ = make_pair(w, h, d, 100 + w)
-    po, pr = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam), orc.PlaneCost(ref_lib, l, r, d, 35, S, lam)
+    po, pr = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam, cc_name=cc), orc.PlaneCost(ref_lib, l, r, d, 35, S, lam, cc_name=cc)
     for a, b in zip(po.info(), pr.info()):
         assert np.array_equal(a, b)
     mo, mr = orc.PatchMatch(orc_lib, l, r, d, 2, seed=11), orc.PatchMatch(ref_lib, l, r, d, 2, seed=11)
