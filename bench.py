@@ -46,6 +46,9 @@ W_HD, H_HD, D_HD = 1920, 1080, 256
 ITERS = 3
 WND = 35
 BYTES_PER_TAP = 19  # 3 B guide pixel + 2 x 8 B cost samples (pre_ss_pc.cc:93,109-110)
+# BASELINE.json configs: (w, h, max_dis, cross-scale S=3 lambda=0.3)
+CONFIGS = {"C1": (450, 375, 60, False), "C2": (450, 375, 60, True), "C3": (1242, 375, 128, True),
+           "C4": (1920, 1080, 256, False), "C4cs": (1920, 1080, 256, True)}
 CPU_CROP = (384, 216)  # bounded CPU sample (w, h), same max_dis: ~10-30 s of CPU work per pass
 
 
@@ -58,10 +61,16 @@ def parse():
     ap.add_argument("--use-cs", action="store_true", help="cross-scale plane cost (PreCSPC, S=3, lambda=0.3)")
     ap.add_argument("--size", default=None, help="WxHxD override (debug only; the headline is 1920x1080x256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json config preset (default: C4, the headline)")
+    ap.add_argument("--cpu-full", action="store_true", help="CPU arm on the whole image instead of the bounded crop (BASELINE.md table)")
     return ap.parse_args()
 
 
 def workload(args):
+    if args.config:
+        w, h, d, cs = CONFIGS[args.config]
+        args.size = f"{w}x{h}x{d}"
+        args.use_cs = cs
     if args.size:
         w, h, d = (int(v) for v in args.size.lower().split("x"))
     else:
@@ -92,10 +101,13 @@ def cpu_run(l, r, d, use_cs, nthreads):
     return t, kind
 
 
+FULL_CPU = {"on": False}
+
+
 def cpu_sample(w, h, d, seed):
     from crossscalepatchmatch_b200.synth import make_pair
 
-    cw, ch = min(CPU_CROP[0], w), min(CPU_CROP[1], h)
+    cw, ch = (w, h) if FULL_CPU["on"] else (min(CPU_CROP[0], w), min(CPU_CROP[1], h))
     l, r, _ = make_pair(w, h, d, seed)
     x0, y0 = (w - cw) // 2, (h - ch) // 2
     return np.ascontiguousarray(l[y0:y0 + ch, x0:x0 + cw]), np.ascontiguousarray(r[y0:y0 + ch, x0:x0 + cw]), cw, ch
@@ -321,6 +333,7 @@ def run_b200(args):
 
 def main():
     args = parse()
+    FULL_CPU["on"] = args.cpu_full
     if args.impl == "reference":
         run_reference(args)
     else:
