@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcspm_b200.so")
+# CSPM_LIB_PATH: load an alternative build of the same ABI (kernel-variant experiments)
+LIB_PATH = os.environ.get("CSPM_LIB_PATH") or os.path.join(_HERE, "libcspm_b200.so")
 
 OK, EINVAL, ENODEV, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SCHEDULE_RASTER, SCHEDULE_REDBLACK = 0, 1

@@ -12,7 +12,7 @@
 // because every pixel has only one live candidate at a time.)
 #pragma once
 
-constexpr int kSpThreads = 768;
+constexpr int kSpThreads = 640;
 constexpr int kSpCtasPerSm = 1;
 constexpr int kSpTasks = 16;  // pixels per CTA per pass: one producer warp per pixel at least
 constexpr int kSpRows = 5;      // window rows per pipeline chunk (WND = 35)
