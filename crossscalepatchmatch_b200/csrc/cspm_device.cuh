@@ -10,6 +10,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Build-time tuning knobs (kernel-variant experiments; the defaults are the measured best).
+#ifndef CSPM_SP_RING
+#define CSPM_SP_RING 16
+#endif
+#ifndef CSPM_TAP_UNROLL
+#define CSPM_TAP_UNROLL 3
+#endif
+#ifndef CSPM_BULK_BY
+#define CSPM_BULK_BY 24
+#endif
+#define CSPM_PRAGMA_(x) _Pragma(#x)
+#define CSPM_UNROLL(n) CSPM_PRAGMA_(unroll n)
+
 namespace cspm {
 
 constexpr int kMaxScales = 8;
@@ -31,6 +44,7 @@ struct ScaleDev {
   int pad, pitch;              // elements; row r, column x lives at r*pitch + pad + x
   const uint32_t* color[2];    // B | G<<8 | R<<16 (8-bit originals; byte 3 = 0)
   const double* grad[2];       // Sobel-x of float gray, f64 (cc/grd_cc.cpp:70-77)
+  const unsigned long long* cg[2];  // GRD only: colour and gradient of a pixel in ONE 64-bit word (see cg_* below)
   const uint32_t* cen_hi[2];   // CEN only: bits 64..79 of the 80-bit census code; bits 0..63 live in grad[] (as raw u64)
   double max_cost[2];          // max over the whole raw cost volume, pre_ss_pc.cc:51-58
 };
@@ -46,6 +60,7 @@ struct PcDev {
   const double* lut_c;         // [kLutC]
   const double* lut_rep;       // [766*16 + kLutC]: weight table replicated 16x, then the colour table (bulk kernels)
   double k_grd;                // (1 - ALPHA), evaluated in double on the host
+  double k_grd27;              // k_grd * 2^-27 (exact), for gradient differences carried as dG * 2^27 (packed GRD layout)
 };
 
 // ------------------------------------------------------------ strict f64 ops
@@ -158,8 +173,10 @@ struct RawCtx {
   const uint32_t* col_o;  // other view, padded
   const double* grd_o;    // GRD: x-gradient; CEN: census bits 0..63 (raw u64 stored in the f64 slot)
   const uint32_t* hi_o;   // CEN: census bits 64..79
+  const unsigned long long* cg_o;  // GRD: packed colour + gradient of the other view
   const double* lut_c;
   double k_grd;
+  double k_grd27;
   int dir;  // partner x = q_x + dir*d : -1 for the left view, +1 for the right view
   int w;    // CEN: image width (partner outside the image costs CENCUS_BIT)
 };
@@ -168,6 +185,46 @@ struct RawCtx {
 __device__ __forceinline__ double abs_min2(double x) {
   const double ax = fabs(x);
   return ax > 2.0 ? 2.0 : ax;
+}
+// Packed GRD pixel.  The float-gray x-gradient G = g[x+1] - g[x-1] of 8-bit images is always an integer
+// multiple of 2^-27 with |G| <= 510 (each f32 gray R*0.299f + G*0.587f + B*0.114f is a multiple of 2^-27 no
+// larger than 255; k_pack verifies it for every pixel), so n = G * 2^27 + 2^37 is a non-negative 38-bit
+// integer.  One 64-bit word per pixel:
+//     bits  0..37  n            bits 40..47 B    48..55 G    56..63 R
+// One 64-bit load per pixel replaces a 32-bit colour load plus a 64-bit gradient load (the bulk kernels are
+// bound by LSU issue: 6 -> 3 loads per tap), and decoding needs no conversion instruction:
+//   * gradient: byte 0 of hi under 0x433000.. (one PRMT) over the untouched low word is the bit pattern of the double
+//     2^52 + n (n sits in the low mantissa bits).  The difference of two such doubles is the exact integer
+//     (G_q - G_p) * 2^27; the clamp min(|dG|, TAU_GRD = 2) becomes min(|.|, 2^28), and the product with
+//     k_grd * 2^-27 rounds exactly like k_grd * min(|dG|, 2) (power-of-two scalings, same real product).
+//   * colour: hi & 0xFFFFFF00 keeps B,G,R in bytes 1..3 with byte 0 clear on both operands, so the 4-byte
+//     SAD instruction returns the 3-channel L1 distance unchanged.
+constexpr uint32_t kCgColorMask = 0xFFFFFF00u;
+__device__ __forceinline__ uint32_t cg_color_key(uint32_t bgr) { return bgr << 8; }  // unpacked colour -> SAD operand
+struct CgPix {
+  uint32_t key;  // colour in bytes 1..3 (SAD operand)
+  double g;      // 2^52 + G * 2^27 + 2^37
+};
+__device__ __forceinline__ CgPix cg_load(const unsigned long long* cg, int idx) {
+  const uint2 w = *reinterpret_cast<const uint2*>(cg + idx);
+  CgPix p;
+  p.key = w.y & kCgColorMask;
+  p.g = __hiloint2double((int)__byte_perm(w.y, 0x43300000u, 0x7650), (int)w.x);  // byte 0 of hi under the exponent of 2^52: one PRMT
+  return p;
+}
+// min(|x|, 2^28).  (An integer-pipe version on the high word was measured slower: 358 vs 349 ms per HD refine.)
+__device__ __forceinline__ double abs_min_2p28(double x) {
+  const double ax = fabs(x);
+  return ax > 268435456.0 ? 268435456.0 : ax;
+}
+// raw_cost<CC_GRD> on the packed layout: same operations in the same order (cc/grd_cc.cpp:4-19)
+__device__ __forceinline__ double raw_cost_cg(const unsigned long long* cg_o, const double* lut_c, double k_grd27, int idx,
+                                              uint32_t kq, double gq) {
+  const CgPix p = cg_load(cg_o, idx);
+  const int sad = min((int)__vsadu4(kq, p.key), kLutC - 1);
+  const double clr = lut_c[sad];                          // ALPHA * min(sum*0.3333333333, TAU_CLR)
+  const double grd = abs_min_2p28(dsub(gq, p.g));         // min(|lG-rG|, TAU_GRD) * 2^27
+  return dadd(clr, dmul(k_grd27, grd));
 }
 // CC = CC_GRD: cq = packed colour of q, gq = gradient of q (qhi unused).
 // CC = CC_CEN: CenCC raw cost (cc/cen_cc.cc:48-67 / :116-135): Hamming distance of the 80-bit census
@@ -195,17 +252,35 @@ struct TapCtx {
   const uint32_t* col_v;  // this view, padded
   const double* grd_v;
   const uint32_t* hi_v;   // CEN only
+  const unsigned long long* cg_v;  // GRD only: packed colour + gradient of this view
   const double* lut_w;
   RawCtx raw;
   double max_cost;
   int max_disp;
 };
 // the plane-dependent part: wgt * (max_cost | lerp of the two raw costs)
-template <int CC>
-__device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double wgt, double a,
-                                            double q_disp_y) {
-  const double q_disp = dadd(dmul(a, (double)qx), q_disp_y);
+// tap_value_qd takes the plane's disparity at q, q_disp = a*q_x + (b*q_y + c) (pre_ss_pc.cc:88,99), already formed.
+// Iq / gqp: colour and gradient of q as returned by load_guide (GRD: SAD key and packed-layout double).
+// DIR: the view's partner direction when known at compile time (-1 left view, +1 right view), 0 = read t.raw.dir.
+template <int CC, int DIR = 0>
+__device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
+                                               double q_disp) {
   const int fl = __double2int_rz(q_disp);  // static_cast<int>: truncation toward zero
+  if (CC == CC_GRD) {
+    // Branch-free: an out-of-range disparity is clamped for ADDRESSING only (the padded rows make any
+    // d in [1, max_disp] readable) and the reference's max_cost is selected at the end.  Straight-line code
+    // lets the scheduler overlap the loads of the unrolled taps instead of serialising one divergent region
+    // per tap (measured 423 -> 388 ms per HD run); the selected values are the same, so results stay bit-identical.
+    const bool valid = fl > 0 && fl < t.max_disp;
+    const int flc = valid ? fl : 1;
+    const double fw = dsub((double)(flc + 1), q_disp);
+    const int dir = DIR != 0 ? DIR : t.raw.dir;  // compile-time: the second partner load is the first +- 8 bytes
+    const int i0 = row_off + qx + dir * flc;
+    const double c0 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, i0, Iq, gqp);
+    const double c1 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, i0 + dir, Iq, gqp);
+    const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
+    return dmul(wgt, valid ? tmp : t.max_cost);
+  }
   if (fl <= 0 || fl >= t.max_disp) return dmul(wgt, t.max_cost);
   if (CC == CC_IMG) {
     // GrdPC / CSPC tap (grd_pc.cc:147-174, cspc.cc:150-175): interpolate the partner IMAGE linearly at the
@@ -238,15 +313,37 @@ __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx
   const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
   return dmul(wgt, tmp);
 }
+template <int CC, int DIR = 0>
+__device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
+                                            double a, double q_disp_y) {
+  return tap_value_qd<CC, DIR>(t, row_off, qx, Iq, gqp, wgt, dadd(dmul(a, (double)qx), q_disp_y));
+}
+// Guide pixel q of this view.  GRD: the SAD key and the gradient double of the packed word (centre colours
+// compared against it must go through guide_key); other kinds: the plain packed colour.
+template <int CC>
+__device__ __forceinline__ void load_guide(const TapCtx& t, int idx, uint32_t* Iq, double* gqp) {
+  if (CC == CC_GRD) {
+    const CgPix p = cg_load(t.cg_v, idx);
+    *Iq = p.key;
+    *gqp = p.g;
+  } else {
+    *Iq = t.col_v[idx];
+    *gqp = 0.0;
+  }
+}
+template <int CC>
+__device__ __forceinline__ uint32_t guide_key(uint32_t bgr) { return CC == CC_GRD ? cg_color_key(bgr) : bgr; }
 // LWS: log2 of the replication factor of the weight table.  With LWS = 4 every lane reads its own copy
 // (t.lut_w already points at copy lane&15, entries are 16 doubles apart): the data-dependent lookup is
 // then free of shared-memory bank conflicts (measured 3.8 conflict wavefronts per warp-tap otherwise).
-template <int CC, int LWS = 0>
+template <int CC, int LWS = 0, int DIR = 0>
 __device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx, uint32_t Ip, double a,
                                            double q_disp_y) {
-  const uint32_t Iq = t.col_v[row_off + qx];
+  uint32_t Iq;
+  double gqp;
+  load_guide<CC>(t, row_off + qx, &Iq, &gqp);
   const double wgt = t.lut_w[__vsadu4(Ip, Iq) << LWS];
-  return tap_value<CC>(t, row_off, qx, Iq, wgt, a, q_disp_y);
+  return tap_value<CC, DIR>(t, row_off, qx, Iq, gqp, wgt, a, q_disp_y);
 }
 
 __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, const double* lut_w,
@@ -256,7 +353,10 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
   t.col_v = sc.color[v];
   t.grd_v = sc.grad[v];
   t.hi_v = sc.cen_hi[v];
+  t.cg_v = sc.cg[v];
   t.lut_w = lut_w;
+  t.raw.cg_o = sc.cg[1 - v];
+  t.raw.k_grd27 = pc.k_grd27;
   t.raw.col_o = sc.color[1 - v];
   t.raw.grd_o = sc.grad[1 - v];
   t.raw.hi_o = sc.cen_hi[1 - v];
@@ -279,42 +379,56 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 // as the final expression — has reached `bound`, the answer is "no" whatever
 // the remaining taps add, and the (partial) value returned is still >= bound.
 // Pass bound = +inf to get the full sum.  Checked once per window row.
-template <int CC, int LWS = 0>
+// CSM: 1 / 0 = the plane cost is / is not cross-scale, known at compile time (bulk kernels); -1 = read pc.cross_scale.
+// DIR as in tap_value_qd.
+template <int CC, int LWS, int CSM, int DIR>
+__device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& sc, const TapCtx& t, uint32_t Ip, int x0, int x1,
+                                              int y0, int y1, double a, double b, double c, double bound, double cost_prev,
+                                              double w_s) {
+  double cost = 0.0;
+  for (int qy = y0; qy <= y1; ++qy) {
+    const double q_disp_y = dadd(dmul(b, (double)qy), c);
+    const int row_off = qy * sc.pitch + sc.pad;
+    CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread: 3 with 24 warps per SM measured best (HD refine 364 ms; 5 x 16 warps: 381)
+    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR>(t, row_off, qx, Ip, a, q_disp_y));
+    const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
+    const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
+    if (total >= bound) break;
+  }
+  return cost;
+}
+template <int CC, int LWS = 0, int CSM = -1>
 __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int rx, int ry, double a, double b,
                                               double c, const double* lut_w, const double* lut_c, double bound,
                                               double cost_prev, double w_s) {
   const ScaleDev& sc = pc.sc[s];
   const TapCtx t = make_tap_ctx(pc, s, v, lut_w, lut_c);
   const int hw = pc.half_wnd;
-  const uint32_t Ip = t.col_v[ry * sc.pitch + sc.pad + rx];
+  const uint32_t Ip = guide_key<CC>(t.col_v[ry * sc.pitch + sc.pad + rx]);
   const int y0 = max(ry - hw, 0), y1 = min(ry + hw, sc.h - 1);
   const int x0 = max(rx - hw, 0), x1 = min(rx + hw, sc.w - 1);
-  double cost = 0.0;
-  for (int qy = y0; qy <= y1; ++qy) {
-    const double q_disp_y = dadd(dmul(b, (double)qy), c);
-    const int row_off = qy * sc.pitch + sc.pad;
-#pragma unroll 5  // 5 independent taps in flight per thread (35 = 7 x 5): measured 471 -> 425 ms per HD run vs the default 2
-    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS>(t, row_off, qx, Ip, a, q_disp_y));
-    const double total = pc.cross_scale ? dadd(cost_prev, dmul(cost, w_s)) : cost;
-    if (total >= bound) break;
+  if (CC == CC_GRD && CSM >= 0) {  // bulk kernels: the view is CTA-uniform, specialise the partner direction
+    return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s)
+                  : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
   }
-  return cost;
+  return window_rows<CC, LWS, CSM, 0>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
 }
 
 // IPlaneCost::GetPlaneCost: PreSSPC (pre_ss_pc.cc:74-118) or PreCSPC
 // (pre_cs_pc.cc:133-188).  Returns the exact cost if it is < bound, otherwise
 // some value >= bound (see window_cost).
-template <int CC, int LWS = 0>
+template <int CC, int LWS = 0, int CSM = -1>
 __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int ry, const PlaneD& p,
                                              const double* lut_w, const double* lut_c, double bound) {
-  if (!pc.cross_scale) return window_cost<CC, LWS>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
+  const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
+  if (!cross) return window_cost<CC, LWS, CSM>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);
   int cx = rx, cy = ry;
   for (int s = 0; s < pc.scale_num; ++s) {
     PlaneD q = p;
     update_param(q, (double)cx, (double)cy, cur_disp);
-    const double sc_cost = window_cost<CC, LWS>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
+    const double sc_cost = window_cost<CC, LWS, CSM>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
     cost = dadd(cost, dmul(sc_cost, pc.scale_wgt[s]));
     if (cost >= bound) break;
     cy /= 2;
@@ -433,7 +547,8 @@ __device__ __forceinline__ EngineSmem engine_smem(double* dyn) {
 // lane compares its running total with `bound`; once reached, the chain is
 // switched off (its remaining addends are neither produced nor added) and the
 // partial total (>= bound) is returned.
-__device__ unsigned long long g_eng_prof[4];  // diagnostic: {consumer busy, producer warp 0 busy, chunk loop total, -} of CTA gridDim/2
+__device__ unsigned long long g_eng_prof[4];
+  // diagnostic: {consumer busy, producer warp 0 busy, chunk loop total, -} of CTA gridDim/2
 struct PairDesc {  // 64 B, written by the consumer lanes, read (broadcast) by the producers
   double a0, b0, c0, a1, b1, c1;
   int cx, cy;
@@ -470,7 +585,7 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
         } else {
           d.a0 = q.a; d.b0 = q.b; d.c0 = q.c;
           d.cx = cx; d.cy = cy;
-          d.Ip = sc.color[ch_v][cy * sc.pitch + sc.pad + cx];
+          d.Ip = guide_key<CC>(sc.color[ch_v][cy * sc.pitch + sc.pad + cx]);
           d.flags = ch_v | (live ? 2 : 0) | (on_other ? 4 : 0);
         }
       }
@@ -508,6 +623,9 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
               tc.col_v = v ? col1 : col0;
               tc.grd_v = v ? grd1 : grd0;
               tc.hi_v = v ? hi1 : hi0;
+              tc.cg_v = sc.cg[v];
+              tc.raw.cg_o = sc.cg[1 - v];
+              tc.raw.k_grd27 = pc.k_grd27;
               tc.lut_w = sm.lut_w;
               tc.raw.col_o = v ? col0 : col1;
               tc.raw.grd_o = v ? grd0 : grd1;
@@ -519,11 +637,13 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
               tc.max_cost = sc.max_cost[v];
               tc.max_disp = sc.max_disp;
               const int row_off = qy * sc.pitch + sc.pad;
-              const uint32_t Iq = tc.col_v[row_off + qx];
+              uint32_t Iq;
+              double gqp;
+              load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
               const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
               const double qyd = (double)qy;
-              if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
-              if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+              if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+              if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
             }
             buf[(2 * gi) * kStride + kk] = t0;
             buf[(2 * gi + 1) * kStride + kk] = t1;
@@ -579,7 +699,7 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
 // kRing rows).  This removes the per-chunk barriers and the load-quantisation
 // loss of the chunked pipeline (1.3 items per thread per chunk -> 2 rounds).
 // ---------------------------------------------------------------------------
-constexpr int kRing = 12;            // window rows in flight
+constexpr int kRing = CSPM_SP_RING;   // window rows in flight
 constexpr int kRingChain = 37;       // doubles per (row, chain): 35 addends, odd stride -> conflict-free reads
 constexpr int kRingRowDoubles = 32 * kRingChain;
 struct ViewCtx {     // everything a producer needs about (scale, view), copied out of the kernel parameters once
@@ -589,6 +709,8 @@ struct ViewCtx {     // everything a producer needs about (scale, view), copied 
   const double* grd_o;
   const uint32_t* hi_v;   // CEN only
   const uint32_t* hi_o;
+  const unsigned long long* cg_v;  // GRD only
+  const unsigned long long* cg_o;
   double max_cost;
   int dir, pad_;
 };
@@ -646,7 +768,7 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
         } else {
           d.a0 = q.a; d.b0 = q.b; d.c0 = q.c;
           d.cx = cx; d.cy = cy;
-          d.Ip = sc.color[ch_v][cy * sc.pitch + sc.pad + cx];
+          d.Ip = guide_key<CC>(sc.color[ch_v][cy * sc.pitch + sc.pad + cx]);
           d.flags = ch_v | (live ? 2 : 0) | (on_other ? 4 : 0);
         }
       }
@@ -657,6 +779,7 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
         vc.col_v = sc.color[lane]; vc.grd_v = sc.grad[lane];
         vc.col_o = sc.color[1 - lane]; vc.grd_o = sc.grad[1 - lane];
         vc.hi_v = sc.cen_hi[lane]; vc.hi_o = sc.cen_hi[1 - lane];
+        vc.cg_v = sc.cg[lane]; vc.cg_o = sc.cg[1 - lane];
         vc.max_cost = sc.max_cost[lane];
         vc.dir = lane ? 1 : -1;
       }
@@ -689,6 +812,9 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
             tc.col_v = vc.col_v;
             tc.grd_v = vc.grd_v;
             tc.hi_v = vc.hi_v;
+            tc.cg_v = vc.cg_v;
+            tc.raw.cg_o = vc.cg_o;
+            tc.raw.k_grd27 = pc.k_grd27;
             tc.lut_w = sm.lut_w;
             tc.raw.col_o = vc.col_o;
             tc.raw.grd_o = vc.grd_o;
@@ -700,11 +826,13 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
             tc.max_cost = vc.max_cost;
             tc.max_disp = smaxd;
             const int row_off = qy * spitch + spad;
-            const uint32_t Iq = tc.col_v[row_off + qx];
+            uint32_t Iq;
+            double gqp;
+            load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
             const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
             const double qyd = (double)qy;
-            if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
-            if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+            if (flags & 2) t0 = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+            if (flags & 4) t1 = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
           }
           double* slot = sm.ring + (size_t)(r % kRing) * kRingRowDoubles + (2 * gi) * kRingChain + dx;
           slot[0] = t0;

@@ -97,6 +97,15 @@ struct DeviceArena {
     }                                                                 \
   } while (0)
 
+// The same with `constexpr bool CS` bound to the plane cost being cross-scale (PreCSPC / CSPC): the bulk
+// kernels are compiled once per (cost kind, single / cross scale) so the single-scale code carries none of
+// the pyramid state in registers.
+#define CSPM_DISPATCH_CC_CS(kind, cross, ...)                                            \
+  do {                                                                                   \
+    if (cross) { constexpr bool CS = true; CSPM_DISPATCH_CC(kind, __VA_ARGS__); }        \
+    else { constexpr bool CS = false; CSPM_DISPATCH_CC(kind, __VA_ARGS__); }             \
+  } while (0)
+
 struct cspm_cc {
   int kind;  // cspm::CcKind
   std::string name;
@@ -117,6 +126,7 @@ struct cspm_pc {
   mutable cspm_stats_t stats{};
   // Sum over pixels of the in-image window size, per scale (for tap counting).
   uint64_t taps_per_image_eval = 0;
+  uint64_t uid = 0;  // unique per created plane cost (never reused, unlike the pointer)
 };
 
 struct cspm_pm {
@@ -141,4 +151,8 @@ struct cspm_pm {
   cspm::DeviceArena arena;
   cspm_stats_t stats{};
   float stage_ms[6] = {};
+  // uid of the plane cost ALL stored min-costs were computed with (0: unknown — before InitRandomPlane,
+  // after cspm_pm_set_planes, or after stages run with different plane costs).  Only when it matches the
+  // plane cost of the current call may the spatial sweep assume cost == GetPlaneCost(stored plane).
+  uint64_t cost_owner = 0;
 };

@@ -28,6 +28,7 @@ struct PmDev {
   int w, h, max_dis, n_ref, dis_scale;
   uint64_t seed;
   double* st[2];  // 7 planes of w*h: nx ny nz a b c cost
+  int cost_consistent;  // every stored cost is GetPlaneCost(stored plane) under the plane cost of this call
 };
 
 __device__ __forceinline__ PlaneD load_plane(const double* st, size_t n, size_t i) {
@@ -43,9 +44,13 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 }
 
 // ------------------------------------------------------------------- init
-constexpr int kBulkBy = 16;  // bulk kernels: 32 x 16 pixels per CTA, one CTA per SM (98 KB replicated table)
-template <int CC>
-__global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
+#ifndef CSPM_BULK_MINB
+#define CSPM_BULK_MINB 1
+#endif
+constexpr int kBulkBy = CSPM_BULK_BY;  // bulk kernels: 32 x kBulkBy pixels per CTA (98 KB replicated table per CTA)
+constexpr int kBulkMinB = CSPM_BULK_MINB;  // CTAs per SM the register allocation must allow
+template <int CC, bool CS>
+__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_init(PcDev pc, PmDev pm) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
   unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
@@ -66,13 +71,13 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_init(PcDev pc, PmDev pm) {
   p.nx = dmul(rn[0], inv); p.ny = dmul(rn[1], inv); p.nz = dmul(rn[2], inv);
   update_param(p, (double)x, (double)y, z);
   tma_stage_luts_wait(s_mbar);
-  const double cost = plane_cost<CC, kLutRepShift>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
+  const double cost = plane_cost<CC, kLutRepShift, CS ? 1 : 0>(pc, v, x, y, p, s_lut_w, s_lut_c, CUDART_INF);
   store_plane(pm.st[v], (size_t)pm.w * pm.h, (size_t)y * pm.w + x, p, cost);
 }
 
 // ----------------------------------------------------------------- refine
-template <int CC>
-__global__ void __launch_bounds__(32 * kBulkBy, 1) k_refine(PcDev pc, PmDev pm, int iter) {
+template <int CC, bool CS>
+__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
   unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_refine(PcDev pc, PmDev pm, 
     const double inv = ddiv(1.0, denom);
     q.nx = dmul(q.nx, inv); q.ny = dmul(q.ny, inv); q.nz = dmul(q.nz, inv);
     update_param(q, (double)x, (double)y, z);
-    const double cost = plane_cost<CC, kLutRepShift>(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
+    const double cost = plane_cost<CC, kLutRepShift, CS ? 1 : 0>(pc, v, x, y, q, s_lut_w, s_lut_c, cur_cost);
     if (cost < cur_cost) {
       cur = q;
       cur_cost = cost;
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(128) k_spatial_diag(PcDev pc, PmDev pm, int di
       q[c] = cand[c];
       if (pc.cross_scale && has[c]) update_param(q[c], (double)cx, (double)cy, cur_disp[c]);
     }
-    const uint32_t Ip = tc.col_v[cy * sc.pitch + sc.pad + cx];
+    const uint32_t Ip = guide_key<CC>(tc.col_v[cy * sc.pitch + sc.pad + cx]);
     for (int k = threadIdx.x; k < 2 * wtaps; k += blockDim.x) {
       const int c = k / wtaps, tap = k - c * wtaps;
       if (!has[c]) continue;
@@ -217,8 +222,8 @@ __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, in
   *q = o;
   update_param(*q, (double)*cor_x, (double)y, disp);
 }
-template <int CC>
-__global__ void __launch_bounds__(32 * kBulkBy, 1) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
+template <int CC, bool CS>
+__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, 1) k_view_eval(PcDev pc, PmDev p
     // a proposal can only win if it beats the target's cost at the start of this pass
     const double bound = pm.st[v][6 * (size_t)pm.w * pm.h + (size_t)y * pm.w + cor_x];
     tma_stage_luts_wait(s_mbar);
-    const double cost = plane_cost<CC, kLutRepShift>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
+    const double cost = plane_cost<CC, kLutRepShift, CS ? 1 : 0>(pc, v, cor_x, y, q, s_lut_w, s_lut_c, bound);
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;
     cand_tx[i] = cor_x;
@@ -398,6 +403,7 @@ static PmDev pm_dev(const cspm_pm* pm) {
   d.w = pm->w; d.h = pm->h; d.max_dis = pm->max_dis; d.n_ref = pm->n_ref; d.dis_scale = pm->dis_scale;
   d.seed = pm->seed;
   d.st[0] = pm->st[0]; d.st[1] = pm->st[1];
+  d.cost_consistent = 0;
   return d;
 }
 
@@ -413,17 +419,25 @@ static void bulk_smem(K kern) {
   CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes));
 }
 
+// Stored costs stay attributable to ONE plane cost only while every cost-writing stage uses that one.
+static void note_cost_writer(cspm_pm* pm, const cspm_pc* pc, bool rewrites_all) {
+  if (rewrites_all) pm->cost_owner = pc->uid;
+  else if (pm->cost_owner != pc->uid) pm->cost_owner = 0;
+}
+
 static void run_init(cspm_pm* pm, const cspm_pc* pc) {
+  note_cost_writer(pm, pc, true);
   dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_init<CC>); k_init<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm)));
+  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_init<CC, CS>); k_init<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm)));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
 }
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  note_cost_writer(pm, pc, false);
   dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_refine<CC>); k_refine<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
+  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_refine<CC, CS>); k_refine<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
@@ -432,7 +446,9 @@ static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
 static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const int rev = (iter % 2 == 0) ? 0 : 1;
   const int wnd = 2 * pc->dev.half_wnd + 1;
+  note_cost_writer(pm, pc, false);
   PmDev d = pm_dev(pm);
+  d.cost_consistent = pm->cost_owner == pc->uid;
   PcDev pcd = pc->dev;
   static const bool force_diag = [] {
     const char* e = getenv("CSPM_SPATIAL");
@@ -482,13 +498,14 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
 
 static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const int rev = (iter % 2 == 0) ? 0 : 1;
+  note_cost_writer(pm, pc, false);
   const PmDev d = pm_dev(pm);
   const size_t n = (size_t)pm->w * pm->h;
   for (int v = 0; v < 2; ++v) {
     k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
     dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy);
-    CSPM_DISPATCH_CC(pc->dev.cc_kind, bulk_smem(k_view_eval<CC>);
-                     k_view_eval<CC><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter));
+    CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_view_eval<CC, CS>);
+                     k_view_eval<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter));
     dim3 g1((pm->w + 127) / 128, pm->h);
     k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
     k_view_commit<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->win);
@@ -720,6 +737,7 @@ int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const doub
     }
     CSPM_CUDA(cudaMemcpyAsync(pm->st[view], h.data(), sizeof(double) * 7 * n, cudaMemcpyHostToDevice, pm->stream));
     CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+    pm->cost_owner = 0;  // caller-supplied costs: no longer known to be GetPlaneCost of the stored planes
   });
 }
 

@@ -12,7 +12,18 @@
 // because every pixel has only one live candidate at a time.)
 #pragma once
 
-constexpr int kSpThreads = 640;
+#ifndef CSPM_SP_THREADS
+#define CSPM_SP_THREADS 640
+#endif
+#ifndef CSPM_SP_LEANFENCE
+#define CSPM_SP_LEANFENCE 1
+#endif
+#ifndef CSPM_SPATIAL_DEDUP
+#define CSPM_SPATIAL_DEDUP 1
+#endif
+__device__ __forceinline__ bool bits_eq(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+
+constexpr int kSpThreads = CSPM_SP_THREADS;
 constexpr int kSpCtasPerSm = 1;
 constexpr int kSpTasks = 16;  // pixels per CTA per pass: one producer warp per pixel at least
 constexpr int kSpRows = 5;      // window rows per pipeline chunk (WND = 35)
@@ -70,7 +81,9 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(barrier_ctr + 32 * o) : "memory");
         } while ((int)seen < diag - 1);
       }
+#if !CSPM_SP_LEANFENCE
       __threadfence();
+#endif
     }
     __syncthreads();
     for (int base = 0; base < ntasks_mine; base += kSpTasks) {
@@ -98,7 +111,34 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
           ch_plane.a = __ldcg(st + 3 * n + j); ch_plane.b = __ldcg(st + 4 * n + j); ch_plane.c = __ldcg(st + 5 * n + j);
         }
         if (cc == 0) ch_min = __ldcg(st + 6 * n + ch_idx);
+#if CSPM_SPATIAL_DEDUP
+        // Exact shortcut 1: a candidate whose six plane numbers are bitwise the pixel's own re-evaluates to
+        // exactly min_cost (the stored cost is always GetPlaneCost of the stored plane), and `cost < min_cost`
+        // (cs_patchmatch.cc:201,209) is false: not evaluated at all.
+        if (ch_on && pm.cost_consistent) {
+          const bool own = bits_eq(ch_plane.a, __ldcg(st + 3 * n + ch_idx)) && bits_eq(ch_plane.b, __ldcg(st + 4 * n + ch_idx)) &&
+                           bits_eq(ch_plane.c, __ldcg(st + 5 * n + ch_idx)) && bits_eq(ch_plane.nx, __ldcg(st + ch_idx)) &&
+                           bits_eq(ch_plane.ny, __ldcg(st + n + ch_idx)) && bits_eq(ch_plane.nz, __ldcg(st + 2 * n + ch_idx));
+          if (own) ch_on = false;
+        }
+#endif
       }
+#if CSPM_SPATIAL_DEDUP
+      // Exact shortcut 2: the y-neighbour carries the same plane as the x-neighbour (common once a plane has
+      // swept a region).  Its cost equals the x-candidate's: if that one was accepted the minimum IS that
+      // cost, otherwise it was >= the minimum — either way `cost < min_cost` fails, so it is not evaluated.
+      if (consumer) {
+        // (every lane executes every shuffle: no short-circuit evaluation here)
+        bool same = ch_on & (__shfl_xor_sync(0xffffffffu, (int)ch_on, 1) != 0);
+        same &= bits_eq(ch_plane.a, __shfl_xor_sync(0xffffffffu, ch_plane.a, 1));
+        same &= bits_eq(ch_plane.b, __shfl_xor_sync(0xffffffffu, ch_plane.b, 1));
+        same &= bits_eq(ch_plane.c, __shfl_xor_sync(0xffffffffu, ch_plane.c, 1));
+        same &= bits_eq(ch_plane.nx, __shfl_xor_sync(0xffffffffu, ch_plane.nx, 1));
+        same &= bits_eq(ch_plane.ny, __shfl_xor_sync(0xffffffffu, ch_plane.ny, 1));
+        same &= bits_eq(ch_plane.nz, __shfl_xor_sync(0xffffffffu, ch_plane.nz, 1));
+        if (cc == 1 && same) ch_on = false;
+      }
+#endif
       // both candidates must beat the pixel's cost at the start of the step (cs_patchmatch.cc:201,209)
       const double ch_bound = __shfl_sync(0xffffffffu, ch_min, lane & ~1);
       SP_PROF(0);
@@ -120,7 +160,9 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
         const int my_best = cc == 0 ? best : best_up;
         if (ti_c < nt && my_best == cc) {  // the lane that owns the winning candidate writes it
           store_plane(pm.st[ch_v], n, ch_idx, ch_plane, ch_cost);
+#if !CSPM_SP_LEANFENCE
           __threadfence();
+#endif
         }
       }
       SP_PROF(2);
@@ -128,7 +170,10 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
     // publish: every writer fenced its stores; one release store per CTA and diagonal
     __syncthreads();
     if (threadIdx.x == 0) {
+#if !CSPM_SP_LEANFENCE
       __threadfence();
+#endif
+      // release is cumulative: the winners' plane stores happen-before it through the CTA barrier above
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(barrier_ctr + 32 * blockIdx.x), "r"((unsigned int)diag) : "memory");
     }
     SP_PROF(3);

@@ -5,6 +5,7 @@
 //
 // Reference: CSPM/cc/grd_cc.cpp, CSPM/plane_cost/pre_ss_pc.cc:12-65,
 // CSPM/plane_cost/pre_cs_pc.cc:12-115.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -59,24 +60,34 @@ __device__ __forceinline__ float gray_of_bgr8(const uint8_t* p) {
 
 // K1a: dense BGR8 -> padded packed colour + padded f64 x-gradient
 // (Sobel ksize=1, REFLECT_101: exactly 0 in the first and last column).
+// cg (GRD only, else null): the same two values in one 64-bit word, (G * 2^27 + 2^37) | colour << 40 — see
+// cspm_device.cuh "Packed GRD pixel".  *inexact counts pixels whose gradient is not an integer multiple of
+// 2^-27 (cannot happen for float gray of 8-bit images; the host refuses to continue if it ever does).
 __global__ void k_pack(const uint8_t* __restrict__ bgr, int w, int h, int pad, int pitch,
-                       uint32_t* __restrict__ color, double* __restrict__ grad) {
+                       uint32_t* __restrict__ color, double* __restrict__ grad, unsigned long long* __restrict__ cg,
+                       unsigned long long* __restrict__ inexact) {
   const int xp = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (xp >= pitch) return;
   const int x = xp - pad;
   const size_t o = (size_t)y * pitch + xp;
-  if (x < 0 || x >= w) {
-    color[o] = 0x00030303u;  // BORDER_THRES for every channel (cc/grd_cc.cpp:21-35)
-    grad[o] = 3.0;
-    return;
+  uint32_t c = 0x00030303u;  // BORDER_THRES for every channel (cc/grd_cc.cpp:21-35)
+  double g = 3.0;
+  if (x >= 0 && x < w) {
+    const uint8_t* row = bgr + (size_t)y * 3 * w;
+    const uint8_t* p = row + 3 * x;
+    c = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    g = 0.0;
+    if (x > 0 && x < w - 1) g = __dsub_rn((double)gray_of_bgr8(p + 3), (double)gray_of_bgr8(p - 3));
   }
-  const uint8_t* row = bgr + (size_t)y * 3 * w;
-  const uint8_t* p = row + 3 * x;
-  color[o] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-  double g = 0.0;
-  if (x > 0 && x < w - 1) g = __dsub_rn((double)gray_of_bgr8(p + 3), (double)gray_of_bgr8(p - 3));
+  color[o] = c;
   grad[o] = g;
+  if (cg) {
+    const double scaled = __dmul_rn(g, 134217728.0);  // * 2^27: exact
+    const long long gi = __double2ll_rn(scaled);
+    if (__ll2double_rn(gi) != scaled || gi >= (1ll << 37) || gi < -(1ll << 37)) atomicAdd(inexact, 1ull);
+    cg[o] = (unsigned long long)(gi + (1ll << 37)) | ((unsigned long long)c << 40);
+  }
 }
 
 // K1a': the same for GrdPC / CSPC (grd_pc.cc:37-40): cvtColor(BGR2GRAY) on 8 bits (14-bit fixed point)
@@ -351,6 +362,8 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
   use_device(device);
 
   cspm_pc* pc = new cspm_pc();
+  static std::atomic<uint64_t> next_uid{1};
+  pc->uid = next_uid.fetch_add(1);
   try {
     pc->device = device;
     pc->wnd_size = wnd_size;
@@ -364,6 +377,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     D.scale_num = pc->scale_num;
     D.half_wnd = wnd_size / 2;
     D.k_grd = 1 - 0.1;  // (1 - ALPHA), cc/grd_cc.cpp:18
+    D.k_grd27 = std::ldexp(D.k_grd, -27);  // exact; pairs with gradient differences carried as dG * 2^27
 
     // lookup tables (host libm exp, exactly as pre_ss_pc.cc:61-64 builds them)
     std::vector<double> lut_w(kLutW), lut_c(kLutC);
@@ -392,6 +406,11 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
       D.lut_rep = d_rep;
     }
 
+    // scratch: raw-cost maxima [2 * kMaxScales] + the packed-layout exactness counter
+    unsigned long long* d_max = pc->arena.alloc<unsigned long long>(2 * kMaxScales + 1);
+    unsigned long long* d_inexact = d_max + 2 * kMaxScales;
+    CSPM_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * (2 * kMaxScales + 1), st));
+
     // pyramid of dense BGR images (pre_cs_pc.cc:42-49)
     int sw = w, sh = h, sd = max_disp;
     for (int s = 0; s < pc->scale_num; ++s) {
@@ -418,12 +437,14 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
         }
         uint32_t* color = pc->arena.alloc<uint32_t>((size_t)S.pitch * sh);
         double* grad = pc->arena.alloc<double>((size_t)S.pitch * sh);
+        unsigned long long* cg = cc->kind == CC_GRD ? pc->arena.alloc<unsigned long long>((size_t)S.pitch * sh) : nullptr;
         dim3 g((S.pitch + 127) / 128, sh);
         if (cc->kind == CC_IMG) k_pack_img<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad);
-        else k_pack<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad);
+        else k_pack<<<g, 128, 0, st>>>(pc->d_bgr[v][s], sw, sh, S.pad, S.pitch, color, grad, cg, d_inexact);
         pc->stats.kernel_launches++;
         S.color[v] = color;
         S.grad[v] = grad;
+        S.cg[v] = cg;
         S.cen_hi[v] = nullptr;
         if (cc->kind == CC_CEN) {  // census code: bits 0..63 replace the gradient array, bits 64..79 in cen_hi
           uint8_t* g8 = pc->arena.alloc<uint8_t>((size_t)sw * sh);
@@ -440,8 +461,6 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     CSPM_CUDA(cudaGetLastError());
 
     // raw-cost maxima (pre_ss_pc.cc:51-58 / pre_cs_pc.cc:75-82)
-    unsigned long long* d_max = pc->arena.alloc<unsigned long long>(2 * kMaxScales);
-    CSPM_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * 2 * kMaxScales, st));
     for (int s = 0; s < pc->scale_num && cc->kind != CC_IMG; ++s)
       for (int v = 0; v < 2; ++v) {
         dim3 g((D.sc[s].w + 127) / 128, D.sc[s].h);
@@ -450,9 +469,11 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
         pc->stats.kernel_launches++;
       }
     CSPM_CUDA(cudaGetLastError());
-    unsigned long long h_max[2 * kMaxScales];
+    unsigned long long h_max[2 * kMaxScales + 1];
     CSPM_CUDA(cudaMemcpyAsync(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
     CSPM_CUDA(cudaStreamSynchronize(st));
+    if (h_max[2 * kMaxScales] != 0)
+      throw Error(CSPM_EUNSUPPORTED, "internal: image gradient not representable in the packed GRD layout");
     for (int s = 0; s < pc->scale_num; ++s)
       for (int v = 0; v < 2; ++v) {
         double m;
