@@ -15,7 +15,7 @@
 #define CSPM_SP_RING 16
 #endif
 #ifndef CSPM_TAP_UNROLL
-#define CSPM_TAP_UNROLL 3
+#define CSPM_TAP_UNROLL 5
 #endif
 #ifndef CSPM_BULK_BY
 #define CSPM_BULK_BY 24
@@ -61,6 +61,10 @@ struct PcDev {
   const double* lut_rep;       // [766*16 + kLutC]: weight table replicated 16x, then the colour table (bulk kernels)
   double k_grd;                // (1 - ALPHA), evaluated in double on the host
   double k_grd27;              // k_grd * 2^-27 (exact), for gradient differences carried as dG * 2^27 (packed GRD layout)
+  uint32_t cg_exp_hi;          // 0x43300000 (high word of 2^52).  A kernel parameter rather than a literal so that
+                               // the PRMT that rebuilds the gradient double takes it from the constant bank and
+                               // keeps its selector as the immediate (as a literal, ptxas re-materialises the
+                               // selector register before almost every PRMT: +3 moves per tap)
 };
 
 // ------------------------------------------------------------ strict f64 ops
@@ -177,6 +181,7 @@ struct RawCtx {
   const double* lut_c;
   double k_grd;
   double k_grd27;
+  uint32_t cg_exp_hi;
   int dir;  // partner x = q_x + dir*d : -1 for the left view, +1 for the right view
   int w;    // CEN: image width (partner outside the image costs CENCUS_BIT)
 };
@@ -205,11 +210,11 @@ struct CgPix {
   uint32_t key;  // colour in bytes 1..3 (SAD operand)
   double g;      // 2^52 + G * 2^27 + 2^37
 };
-__device__ __forceinline__ CgPix cg_load(const unsigned long long* cg, int idx) {
+__device__ __forceinline__ CgPix cg_load(const unsigned long long* cg, int idx, uint32_t exp_hi) {
   const uint2 w = *reinterpret_cast<const uint2*>(cg + idx);
   CgPix p;
   p.key = w.y & kCgColorMask;
-  p.g = __hiloint2double((int)__byte_perm(w.y, 0x43300000u, 0x7650), (int)w.x);  // byte 0 of hi under the exponent of 2^52: one PRMT
+  p.g = __hiloint2double((int)__byte_perm(w.y, exp_hi, 0x7650), (int)w.x);  // byte 0 of hi under the exponent of 2^52: one PRMT
   return p;
 }
 // min(|x|, 2^28).  (An integer-pipe version on the high word was measured slower: 358 vs 349 ms per HD refine.)
@@ -217,14 +222,19 @@ __device__ __forceinline__ double abs_min_2p28(double x) {
   const double ax = fabs(x);
   return ax > 268435456.0 ? 268435456.0 : ax;
 }
-// raw_cost<CC_GRD> on the packed layout: same operations in the same order (cc/grd_cc.cpp:4-19)
-__device__ __forceinline__ double raw_cost_cg(const unsigned long long* cg_o, const double* lut_c, double k_grd27, int idx,
-                                              uint32_t kq, double gq) {
-  const CgPix p = cg_load(cg_o, idx);
+// raw_cost<CC_GRD> on the packed layout (cc/grd_cc.cpp:4-19).  The gradient term k_grd * min(|dG|, TAU_GRD) is
+// formed as min(|k * dG|, k * TAU_GRD): multiplication by k > 0 is monotone under round-to-nearest and
+// commutes with |.|, so both sides of the min are the correctly rounded products the reference computes in
+// either case — and the absolute value rides as an operand modifier on the final add (one FP64 op less).
+__device__ __forceinline__ double raw_cost_cg(const unsigned long long* cg_o, const double* lut_c, double k_grd27,
+                                              uint32_t exp_hi, int idx, uint32_t kq, double gq) {
+  const CgPix p = cg_load(cg_o, idx, exp_hi);
   const int sad = min((int)__vsadu4(kq, p.key), kLutC - 1);
   const double clr = lut_c[sad];                          // ALPHA * min(sum*0.3333333333, TAU_CLR)
-  const double grd = abs_min_2p28(dsub(gq, p.g));         // min(|lG-rG|, TAU_GRD) * 2^27
-  return dadd(clr, dmul(k_grd27, grd));
+  const double kd = dmul(k_grd27, dsub(gq, p.g));         // (1-ALPHA) * (lG-rG), signed
+  const double k_tau = dmul(k_grd27, 268435456.0);        // (1-ALPHA) * TAU_GRD (exact power-of-two scaling)
+  const double grd = fabs(kd) > k_tau ? k_tau : kd;
+  return dadd(clr, fabs(grd));
 }
 // CC = CC_GRD: cq = packed colour of q, gq = gradient of q (qhi unused).
 // CC = CC_CEN: CenCC raw cost (cc/cen_cc.cc:48-67 / :116-135): Hamming distance of the 80-bit census
@@ -262,7 +272,9 @@ struct TapCtx {
 // tap_value_qd takes the plane's disparity at q, q_disp = a*q_x + (b*q_y + c) (pre_ss_pc.cc:88,99), already formed.
 // Iq / gqp: colour and gradient of q as returned by load_guide (GRD: SAD key and packed-layout double).
 // DIR: the view's partner direction when known at compile time (-1 left view, +1 right view), 0 = read t.raw.dir.
-template <int CC, int DIR = 0>
+// ALLVALID: the caller has proved that trunc(q_disp) lies in [1, max_disp) for every tap of the window
+// (GRD only): the validity test and the max_cost select are compiled out.
+template <int CC, int DIR = 0, bool ALLVALID = false>
 __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
                                                double q_disp) {
   const int fl = __double2int_rz(q_disp);  // static_cast<int>: truncation toward zero
@@ -271,15 +283,15 @@ __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int
     // d in [1, max_disp] readable) and the reference's max_cost is selected at the end.  Straight-line code
     // lets the scheduler overlap the loads of the unrolled taps instead of serialising one divergent region
     // per tap (measured 423 -> 388 ms per HD run); the selected values are the same, so results stay bit-identical.
-    const bool valid = fl > 0 && fl < t.max_disp;
-    const int flc = valid ? fl : 1;
+    const bool valid = ALLVALID || (fl > 0 && fl < t.max_disp);
+    const int flc = ALLVALID ? fl : (valid ? fl : 1);
     const double fw = dsub((double)(flc + 1), q_disp);
     const int dir = DIR != 0 ? DIR : t.raw.dir;  // compile-time: the second partner load is the first +- 8 bytes
     const int i0 = row_off + qx + dir * flc;
-    const double c0 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, i0, Iq, gqp);
-    const double c1 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, i0 + dir, Iq, gqp);
+    const double c0 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0, Iq, gqp);
+    const double c1 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0 + dir, Iq, gqp);
     const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
-    return dmul(wgt, valid ? tmp : t.max_cost);
+    return dmul(wgt, ALLVALID ? tmp : (valid ? tmp : t.max_cost));
   }
   if (fl <= 0 || fl >= t.max_disp) return dmul(wgt, t.max_cost);
   if (CC == CC_IMG) {
@@ -313,17 +325,17 @@ __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int
   const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
   return dmul(wgt, tmp);
 }
-template <int CC, int DIR = 0>
+template <int CC, int DIR = 0, bool ALLVALID = false>
 __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
                                             double a, double q_disp_y) {
-  return tap_value_qd<CC, DIR>(t, row_off, qx, Iq, gqp, wgt, dadd(dmul(a, (double)qx), q_disp_y));
+  return tap_value_qd<CC, DIR, ALLVALID>(t, row_off, qx, Iq, gqp, wgt, dadd(dmul(a, (double)qx), q_disp_y));
 }
 // Guide pixel q of this view.  GRD: the SAD key and the gradient double of the packed word (centre colours
 // compared against it must go through guide_key); other kinds: the plain packed colour.
 template <int CC>
 __device__ __forceinline__ void load_guide(const TapCtx& t, int idx, uint32_t* Iq, double* gqp) {
   if (CC == CC_GRD) {
-    const CgPix p = cg_load(t.cg_v, idx);
+    const CgPix p = cg_load(t.cg_v, idx, t.raw.cg_exp_hi);
     *Iq = p.key;
     *gqp = p.g;
   } else {
@@ -336,14 +348,14 @@ __device__ __forceinline__ uint32_t guide_key(uint32_t bgr) { return CC == CC_GR
 // LWS: log2 of the replication factor of the weight table.  With LWS = 4 every lane reads its own copy
 // (t.lut_w already points at copy lane&15, entries are 16 doubles apart): the data-dependent lookup is
 // then free of shared-memory bank conflicts (measured 3.8 conflict wavefronts per warp-tap otherwise).
-template <int CC, int LWS = 0, int DIR = 0>
+template <int CC, int LWS = 0, int DIR = 0, bool ALLVALID = false>
 __device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx, uint32_t Ip, double a,
                                            double q_disp_y) {
   uint32_t Iq;
   double gqp;
   load_guide<CC>(t, row_off + qx, &Iq, &gqp);
   const double wgt = t.lut_w[__vsadu4(Ip, Iq) << LWS];
-  return tap_value<CC, DIR>(t, row_off, qx, Iq, gqp, wgt, a, q_disp_y);
+  return tap_value<CC, DIR, ALLVALID>(t, row_off, qx, Iq, gqp, wgt, a, q_disp_y);
 }
 
 __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, const double* lut_w,
@@ -357,6 +369,7 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
   t.lut_w = lut_w;
   t.raw.cg_o = sc.cg[1 - v];
   t.raw.k_grd27 = pc.k_grd27;
+  t.raw.cg_exp_hi = pc.cg_exp_hi;
   t.raw.col_o = sc.color[1 - v];
   t.raw.grd_o = sc.grad[1 - v];
   t.raw.hi_o = sc.cen_hi[1 - v];
@@ -381,7 +394,7 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 // Pass bound = +inf to get the full sum.  Checked once per window row.
 // CSM: 1 / 0 = the plane cost is / is not cross-scale, known at compile time (bulk kernels); -1 = read pc.cross_scale.
 // DIR as in tap_value_qd.
-template <int CC, int LWS, int CSM, int DIR>
+template <int CC, int LWS, int CSM, int DIR, bool ALLVALID = false>
 __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& sc, const TapCtx& t, uint32_t Ip, int x0, int x1,
                                               int y0, int y1, double a, double b, double c, double bound, double cost_prev,
                                               double w_s) {
@@ -389,8 +402,8 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
   for (int qy = y0; qy <= y1; ++qy) {
     const double q_disp_y = dadd(dmul(b, (double)qy), c);
     const int row_off = qy * sc.pitch + sc.pad;
-    CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread: 3 with 24 warps per SM measured best (HD refine 364 ms; 5 x 16 warps: 381)
-    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR>(t, row_off, qx, Ip, a, q_disp_y));
+    CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread (35 = 7 x 5); 24 warps per SM x 5 taps measured best
+    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
     const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
     const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
     if (total >= bound) break;
@@ -408,6 +421,22 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
   const int y0 = max(ry - hw, 0), y1 = min(ry + hw, sc.h - 1);
   const int x0 = max(rx - hw, 0), x1 = min(rx + hw, sc.w - 1);
   if (CC == CC_GRD && CSM >= 0) {  // bulk kernels: the view is CTA-uniform, specialise the partner direction
+    // The plane's disparity q_disp = a*q_x + (b*q_y + c) is, as computed (rounded products and sums are
+    // monotone), monotone in q_x for fixed q_y and in q_y for fixed q_x, so its extremes over the window
+    // are at the four corners.  If every corner truncates into [1, max_disp) — for every lane of the warp,
+    // so that the warp stays on one code path — no tap of this window can be invalid and the loop without
+    // the validity test / max_cost select is used (5 of ~63 instructions per tap).
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int qx = (k & 1) ? x1 : x0, qy = (k & 2) ? y1 : y0;
+      const int fl = __double2int_rz(dadd(dmul(a, (double)qx), dadd(dmul(b, (double)qy), c)));
+      ok = ok && fl > 0 && fl < t.max_disp;
+    }
+    const bool all_ok = __all_sync(__activemask(), ok);
+    if (all_ok)
+      return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s)
+                    : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
     return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s)
                   : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
   }
@@ -626,6 +655,7 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
               tc.cg_v = sc.cg[v];
               tc.raw.cg_o = sc.cg[1 - v];
               tc.raw.k_grd27 = pc.k_grd27;
+            tc.raw.cg_exp_hi = pc.cg_exp_hi;
               tc.lut_w = sm.lut_w;
               tc.raw.col_o = v ? col0 : col1;
               tc.raw.grd_o = v ? grd0 : grd1;
@@ -815,6 +845,7 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
             tc.cg_v = vc.cg_v;
             tc.raw.cg_o = vc.cg_o;
             tc.raw.k_grd27 = pc.k_grd27;
+            tc.raw.cg_exp_hi = pc.cg_exp_hi;
             tc.lut_w = sm.lut_w;
             tc.raw.col_o = vc.col_o;
             tc.raw.grd_o = vc.grd_o;

@@ -377,6 +377,7 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     D.scale_num = pc->scale_num;
     D.half_wnd = wnd_size / 2;
     D.k_grd = 1 - 0.1;  // (1 - ALPHA), cc/grd_cc.cpp:18
+    D.cg_exp_hi = 0x43300000u;
     D.k_grd27 = std::ldexp(D.k_grd, -27);  // exact; pairs with gradient differences carried as dG * 2^27
 
     // lookup tables (host libm exp, exactly as pre_ss_pc.cc:61-64 builds them)

@@ -149,7 +149,13 @@ int cspm_pm_stage(cspm_pm_t* pm, int stage, int iter, const cspm_pc_t* pc);
 int cspm_pm_get_dis(const cspm_pm_t* pm, int view, uint8_t* out, int out_stride);
 int cspm_pm_set_dis(cspm_pm_t* pm, int view, const uint8_t* in, int in_stride);
 /* Parity export / import of the per-pixel state: normal[h*w*3], param[h*w*3]
- * (a,b,c), min_cost[h*w]; host pointers, any may be NULL on get. */
+ * (a,b,c), min_cost[h*w]; host pointers, any may be NULL on get.
+ * The imported costs need not belong to the imported planes: results stay those
+ * of the reference loops on that state.  (The spatial sweep's "candidate equals
+ * the pixel's own plane, so it cannot win" shortcut is only taken while every
+ * stored cost is known to be GetPlaneCost of its plane under the plane cost of
+ * the current call — i.e. from InitRandomPlane on, with one plane cost — and
+ * set_planes / a different plane cost switch it off.) */
 int cspm_pm_get_planes(const cspm_pm_t* pm, int view, double* normal, double* param, double* min_cost);
 int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const double* param,
                        const double* min_cost);

@@ -199,6 +199,44 @@ def test_stages_bit_exact(cspm, orc_lib, pair, S, lam):
         assert np.array_equal(mo.dis(v), mg.dis(v)), "post-processing"
 
 
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (3, 0.3)])
+def test_spatial_shortcuts_are_exact_on_foreign_state(cspm, orc_lib, pair, S, lam):
+    """The spatial sweep skips (a) a candidate that is bitwise the pixel's own plane and (b) a y-neighbour
+    candidate equal to the x-neighbour's.  (a) is only sound while the stored costs are GetPlaneCost of the
+    stored planes under the SAME plane cost; it must switch itself off for caller-supplied state
+    (cspm_pm_set_planes) and when the plane cost changes between stages.  Large constant-plane regions make
+    both shortcuts fire on (almost) every pixel."""
+    l, r = pair
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam)
+    pg = cspm.PreSSPC(l, r, D, 35, cc) if S == 0 else cspm.PreCSPC(l, r, D, 35, S, cc, lam)
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=3)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=3)
+    rng = np.random.default_rng(5)
+    for v in (0, 1):
+        n = np.zeros((H, W, 3)); n[..., 2] = 1.0            # fronto-parallel everywhere ...
+        prm = np.zeros((H, W, 3)); prm[..., 2] = 5.0
+        prm[:, W // 2:, 2] = 9.0                            # ... two constant regions
+        cost = rng.uniform(0.0, 4000.0, (H, W))             # costs that do NOT belong to the planes
+        mo.set_planes(v, n, prm, cost)
+        mg.set_planes(v, n, prm, cost)
+    for it in range(2):
+        mo.stage(orc.PatchMatch.SPATIAL, it, po)
+        mg.stage(cspm.STAGE_SPATIAL, it, pg)
+        _same_state(mo, mg, f"foreign state, sweep {it}")
+    # consistent state from one plane cost, then a sweep under another one
+    po2 = orc.PlaneCost(orc_lib, l, r, D, 35, 2, 0.5)
+    pg2 = cspm.PreCSPC(l, r, D, 35, 2, cc, 0.5)
+    mo.stage(orc.PatchMatch.INIT, 0, po)
+    mg.stage(cspm.STAGE_INIT, 0, pg)
+    mo.stage(orc.PatchMatch.SPATIAL, 0, po)
+    mg.stage(cspm.STAGE_SPATIAL, 0, pg)
+    _same_state(mo, mg, "own state")
+    mo.stage(orc.PatchMatch.SPATIAL, 1, po2)
+    mg.stage(cspm.STAGE_SPATIAL, 1, pg2)
+    _same_state(mo, mg, "plane cost swapped between stages")
+
+
 @pytest.mark.parametrize("w,h,d,scale,S,lam,iters,pp", [
     (80, 60, 16, 4, 0, 0.0, 3, False),
     (80, 60, 16, 4, 3, 0.3, 2, True),
