@@ -47,10 +47,12 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 #ifndef CSPM_BULK_MINB
 #define CSPM_BULK_MINB 1
 #endif
-constexpr int kBulkBy = CSPM_BULK_BY;  // bulk kernels: 32 x kBulkBy pixels per CTA (98 KB replicated table per CTA)
+constexpr int kBulkBySs = CSPM_BULK_BY;     // bulk kernels: 32 x kBulkBy pixels per CTA (98 KB replicated table per CTA) ...
+constexpr int kBulkByCs = CSPM_BULK_BY_CS;  // ... chosen separately for the cross-scale instantiations (more live state)
+template <bool CS> constexpr int bulk_by() { return CS ? kBulkByCs : kBulkBySs; }
 constexpr int kBulkMinB = CSPM_BULK_MINB;  // CTAs per SM the register allocation must allow
 template <int CC, bool CS>
-__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_init(PcDev pc, PmDev pm) {
+__global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_init(PcDev pc, PmDev pm) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
   unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_init(PcDev pc, PmDe
 
 // ----------------------------------------------------------------- refine
 template <int CC, bool CS>
-__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
+__global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
   unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
@@ -223,7 +225,7 @@ __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, in
   update_param(*q, (double)*cor_x, (double)y, disp);
 }
 template <int CC, bool CS>
-__global__ void __launch_bounds__(32 * kBulkBy, kBulkMinB) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
+__global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
   extern __shared__ __align__(16) double s_dyn[];
   double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
@@ -427,8 +429,8 @@ static void note_cost_writer(cspm_pm* pm, const cspm_pc* pc, bool rewrites_all) 
 
 static void run_init(cspm_pm* pm, const cspm_pc* pc) {
   note_cost_writer(pm, pc, true);
-  dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_init<CC, CS>); k_init<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm)));
+  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = bulk_by<CS>(); dim3 b(32, by), g((pm->w + 31) / 32, (pm->h + by - 1) / by, 2);
+                      bulk_smem(k_init<CC, CS>); k_init<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm)));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pc->taps_per_image_eval;
@@ -436,8 +438,8 @@ static void run_init(cspm_pm* pm, const cspm_pc* pc) {
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
   note_cost_writer(pm, pc, false);
-  dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy, 2);
-  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_refine<CC, CS>); k_refine<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
+  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = bulk_by<CS>(); dim3 b(32, by), g((pm->w + 31) / 32, (pm->h + by - 1) / by, 2);
+                      bulk_smem(k_refine<CC, CS>); k_refine<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
@@ -503,8 +505,8 @@ static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const size_t n = (size_t)pm->w * pm->h;
   for (int v = 0; v < 2; ++v) {
     k_view_begin<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(d, v, pm->tmin, pm->win);
-    dim3 b(32, kBulkBy), g((pm->w + 31) / 32, (pm->h + kBulkBy - 1) / kBulkBy);
-    CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, bulk_smem(k_view_eval<CC, CS>);
+    CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = bulk_by<CS>(); dim3 b(32, by), g((pm->w + 31) / 32, (pm->h + by - 1) / by);
+                     bulk_smem(k_view_eval<CC, CS>);
                      k_view_eval<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, v, pm->cand_cost, pm->cand_tx, pm->tmin, pm->tap_counter));
     dim3 g1((pm->w + 127) / 128, pm->h);
     k_view_resolve<<<g1, 128, 0, pm->stream>>>(d, v, rev, pm->cand_cost, pm->cand_tx, pm->tmin, pm->win);
