@@ -355,16 +355,31 @@ __global__ void k_pp_fill(PmDev pm, uint8_t* dis0, uint8_t* dis1, const int* val
 // in shared memory.  Only VALID neighbours contribute and valid pixels are
 // never rewritten, so reading `dis` while other threads update invalid pixels
 // is order-free; we still read from a snapshot to keep it race-free.
+// The weighted median only touches pixels that failed the left-right check (typically ~10 %): their indices are
+// compacted first (order is irrelevant, every pixel is independent) so that the 16 histogram slots of a CTA are
+// all in use (HD, both views: 37 -> 19 ms).
+__global__ void k_pp_compact(const int* __restrict__ valid, int n, int* __restrict__ list, unsigned int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool take = i < n && !valid[i];
+  const unsigned int m = __ballot_sync(0xffffffffu, take);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (take) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
 __global__ void __launch_bounds__(16) k_pp_wmedian(PmDev pm, int v, const uint8_t* __restrict__ bgr,
                                                    const uint8_t* __restrict__ dis_in, uint8_t* dis_out,
                                                    const int* __restrict__ valid, const double* __restrict__ lut_w,
-                                                   int half_wnd) {
+                                                   int half_wnd, const int* __restrict__ list,
+                                                   const unsigned int* __restrict__ count) {
   __shared__ double hist[16][257];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  if (x >= pm.w) return;
+  const unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  const int pix = list[slot];
+  const int y = pix / pm.w, x = pix - y * pm.w;
   const size_t row = (size_t)y * pm.w;
-  if (valid[row + x]) return;
   double* hs = hist[threadIdx.x];
   for (int d = 0; d < 256; ++d) hs[d] = 0.0;
   const uint8_t* p = bgr + (row + x) * 3;
@@ -531,10 +546,14 @@ static void run_postproc(cspm_pm* pm, const cspm_pc* pc) {
   const size_t n = (size_t)pm->w * pm->h;
   for (int v = 0; v < 2; ++v) {
     CSPM_CUDA(cudaMemcpyAsync(pm->dis_tmp, pm->dis[v], n, cudaMemcpyDeviceToDevice, pm->stream));
-    dim3 g2((pm->w + 15) / 16, pm->h);
-    // WeightedMedian(valid, 35, WMF_GAMMA) — WMF_GAMMA == WGT_GAMMA == 10, same exp table
-    k_pp_wmedian<<<g2, 16, 0, pm->stream>>>(d, v, pm->d_bgr[v], pm->dis_tmp, pm->dis[v], pm->valid[v], pc->dev.lut_w, 35 / 2);
-    pm->stats.kernel_launches++;
+    // invalid pixels -> list (view-propagation scratch is free here: cand_tx holds the list, win[0] its length)
+    CSPM_CUDA(cudaMemsetAsync(pm->win, 0, sizeof(unsigned int), pm->stream));
+    k_pp_compact<<<(unsigned)((n + 255) / 256), 256, 0, pm->stream>>>(pm->valid[v], (int)n, pm->cand_tx, pm->win);
+    // WeightedMedian(valid, 35, WMF_GAMMA) — WMF_GAMMA == WGT_GAMMA == 10, same exp table.  The grid covers the
+    // worst case (every pixel invalid); CTAs beyond the list length exit at once.
+    k_pp_wmedian<<<(unsigned)((n + 15) / 16), 16, 0, pm->stream>>>(d, v, pm->d_bgr[v], pm->dis_tmp, pm->dis[v], pm->valid[v],
+                                                                    pc->dev.lut_w, 35 / 2, pm->cand_tx, pm->win);
+    pm->stats.kernel_launches += 2;
   }
 }
 
