@@ -777,9 +777,9 @@ template <int CC, int NT>
 __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const RingSmem& sm, int nch, bool ch_on, int ch_v,
                                                          int ch_x, int ch_y, const PlaneD& ch_plane, double ch_bound) {
   constexpr int WND = 35, HW = 17;
-  constexpr int kProducers = NT - 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool consumer = warp == NT / 32 - 1;
+  constexpr int kProducers = NT - 32;
   const int npairs = (nch + 1) >> 1;
   const int row_items = npairs * WND;
   volatile int* v_done = sm.ctl->done;
@@ -877,8 +877,9 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
       }
     } else {
       for (int r = 0; r < WND; ++r) {
-        while (v_done[r] < row_items) __nanosleep(20);
+        while (v_done[r] < row_items) __nanosleep(20);  // (a pure spin was measured slower: 225 vs 221 ms per HD run)
         __threadfence_block();
+        const bool was_live = live;
         if (live) {
           const volatile double* tp = sm.ring + (size_t)(r % kRing) * kRingRowDoubles + lane * kRingChain;
 #pragma unroll
@@ -890,14 +891,16 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
 #pragma unroll
             for (int k = 0; k < 12; ++k)
               if (k0 + k < WND) sum = dadd(sum, t[k]);
-          }
+          }  // (requesting the next 12 before adding the current 12 was measured slower: 224 vs 221 ms)
           const double total = pc.cross_scale ? dadd(cost, dmul(sum, pc.scale_wgt[s])) : sum;
           if (total >= ch_bound) live = false;  // rejected for certain: stop this chain
         }
-        const int live_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
-        if (lane < 2 * npairs && !(lane & 1)) {
-          const int f = ch_v | (live ? 2 : 0) | (live_other ? 4 : 0);
-          if (f != sm.pd[lane >> 1].flags) *reinterpret_cast<volatile int*>(&sm.pd[lane >> 1].flags) = f;
+        if (__any_sync(0xffffffffu, was_live != live)) {  // publish only when a chain was switched off in this row
+          const int live_other = __shfl_xor_sync(0xffffffffu, (int)live, 1);
+          if (lane < 2 * npairs && !(lane & 1)) {
+            const int f = ch_v | (live ? 2 : 0) | (live_other ? 4 : 0);
+            if (f != sm.pd[lane >> 1].flags) *reinterpret_cast<volatile int*>(&sm.pd[lane >> 1].flags) = f;
+          }
         }
         __syncwarp();
         if (lane == 0) *v_consumed = r + 1;
