@@ -14,6 +14,14 @@
 #ifndef CSPM_SP_RING
 #define CSPM_SP_RING 16
 #endif
+// -DCSPM_PROFILE_LANES=1: diagnostic build that histograms, per executed window row of the bulk kernels, how many
+// lanes of the warp were still evaluating (read back with cspm_debug_lane_hist; scratch/lane_hist.py).
+#ifndef CSPM_PROFILE_LANES
+#define CSPM_PROFILE_LANES 0
+#endif
+#ifndef CSPM_COOP_LANES
+#define CSPM_COOP_LANES 6
+#endif
 #ifndef CSPM_TAP_UNROLL
 #define CSPM_TAP_UNROLL 5
 #endif
@@ -385,6 +393,8 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
   return t;
 }
 
+__device__ unsigned long long g_lane_hist[33];  // CSPM_PROFILE_LANES: window rows executed with k active lanes
+
 // PreSSPC::GetPlaneCost window at one scale, literal row-major accumulation
 // order (pre_ss_pc.cc:84-116 / pre_cs_pc.cc:151-181).
 //
@@ -397,19 +407,89 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 // Pass bound = +inf to get the full sum.  Checked once per window row.
 // CSM: 1 / 0 = the plane cost is / is not cross-scale, known at compile time (bulk kernels); -1 = read pc.cross_scale.
 // DIR as in tap_value_qd.
+// Cooperative tail (single-scale bulk kernels, coop != nullptr).  Early termination is per lane, so a warp often ends up
+// with a handful of lanes still evaluating while the others idle (HD refinement: 15 % of all executed window
+// rows run with <= 4 of 32 lanes, profiles/r01_lane_hist.txt).  Once at most kCoopLanes lanes of a FULL warp are
+// left, the warp changes shape: for each surviving lane L in turn, all 32 lanes compute the <= 35 addends of
+// L's current window row — lane j takes tap x0_L + j, a second pass the last three — park them in a per-warp
+// shared-memory strip, and lane L alone adds them to its running sum in tap order.  The sum is formed by the
+// same operations in the same order as in the per-lane loop (bit-identical) and the per-row termination test is
+// unchanged.  Measured at HD: refinement 337 -> 328 ms with the switch at <= 6 lanes (2 / 4 / 8: 341 / 334 / 330).
+constexpr int kCoopLanes = CSPM_COOP_LANES;  // switch to the cooperative tail at <= this many live lanes; 0: never
+constexpr int kCoopStride = 64;               // doubles per warp strip (a window row has at most 63 addends)
 template <int CC, int LWS, int CSM, int DIR, bool ALLVALID = false>
 __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& sc, const TapCtx& t, uint32_t Ip, int x0, int x1,
                                               int y0, int y1, double a, double b, double c, double bound, double cost_prev,
-                                              double w_s) {
+                                              double w_s, double* coop = nullptr) {
+  const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
   double cost = 0.0;
-  for (int qy = y0; qy <= y1; ++qy) {
-    const double q_disp_y = dadd(dmul(b, (double)qy), c);
+  if (kCoopLanes == 0 || CSM != 0 || CC != CC_GRD || coop == nullptr) {  // (cross-scale: measured 1 % slower with the tail)
+    for (int qy = y0; qy <= y1; ++qy) {
+      const double q_disp_y = dadd(dmul(b, (double)qy), c);
+      const int row_off = qy * sc.pitch + sc.pad;
+#if CSPM_PROFILE_LANES
+      {
+        const unsigned int m = __activemask();
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&g_lane_hist[__popc(m)], 1ull);
+      }
+#endif
+      CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread (35 = 7 x 5); 24 warps per SM x 5 taps measured best
+      for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
+      const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
+      if (total >= bound) break;
+    }
+    return cost;
+  }
+  // ---- bulk kernels: all lanes of the warp stay in the row loop together (same y0 / y1: one image row per warp)
+  const unsigned int mask = __activemask();
+  const int lane = threadIdx.x & 31;
+  bool done = false;
+  int qy = y0;
+  for (; qy <= y1; ++qy) {
+#if CSPM_PROFILE_LANES
+    {
+      const unsigned int act = __ballot_sync(mask, !done);
+      if (lane == __ffs(mask) - 1) atomicAdd(&g_lane_hist[__popc(act)], 1ull);
+    }
+#endif
+    if (!done) {
+      const double q_disp_y = dadd(dmul(b, (double)qy), c);
+      const int row_off = qy * sc.pitch + sc.pad;
+      CSPM_UNROLL(CSPM_TAP_UNROLL)
+      for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
+      const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
+      if (total >= bound) done = true;
+    }
+    const unsigned int alive = __ballot_sync(mask, !done);
+    if (alive == 0u) return cost;
+    if (mask == 0xffffffffu && __popc(alive) <= kCoopLanes) { ++qy; break; }
+  }
+  // ---- cooperative tail: rows qy .. y1 of the surviving lanes, one lane-row at a time
+  for (; qy <= y1; ++qy) {
+    unsigned int todo = __ballot_sync(mask, !done);
+    if (todo == 0u) break;
     const int row_off = qy * sc.pitch + sc.pad;
-    CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread (35 = 7 x 5); 24 warps per SM x 5 taps measured best
-    for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
-    const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
-    const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
-    if (total >= bound) break;
+    const double my_qdy = dadd(dmul(b, (double)qy), c);
+    while (todo) {
+      const int L = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      const double aL = __shfl_sync(mask, a, L), qdyL = __shfl_sync(mask, my_qdy, L);
+      const uint32_t IpL = __shfl_sync(mask, Ip, L);
+      const int x0L = __shfl_sync(mask, x0, L), nL = __shfl_sync(mask, x1, L) - x0L + 1;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int j = lane + 32 * pass;
+        if (j < nL) coop[j] = tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, x0L + j, IpL, aL, qdyL);
+      }
+      __syncwarp(mask);
+      if (lane == L) {
+        const volatile double* cp = coop;
+        for (int j = 0; j < nL; ++j) cost = dadd(cost, cp[j]);
+        const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
+        if (total >= bound) done = true;
+      }
+      __syncwarp(mask);
+    }
   }
   return cost;
 }
@@ -437,11 +517,13 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
       ok = ok && fl > 0 && fl < t.max_disp;
     }
     const bool all_ok = __all_sync(__activemask(), ok);
+    // per-warp strip for the cooperative tail: behind the colour table and the mbarrier of the bulk layout
+    double* coop = const_cast<double*>(lut_c) + kLutC + 2 + (size_t)threadIdx.y * kCoopStride;
     if (all_ok)
-      return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s)
-                    : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
-    return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s)
-                  : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
+      return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
+                    : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
+    return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
+                  : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
   }
   return window_rows<CC, LWS, CSM, 0>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
 }
@@ -483,7 +565,7 @@ __device__ __forceinline__ void stage_luts(const PcDev& pc, double* s_lut_w, dou
 constexpr int kLutWUsed = 766;
 constexpr int kLutRepShift = 4;
 constexpr size_t kBulkLutBytes = sizeof(double) * ((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);  // 98 304 B, multiple of 16
-constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16;  // + the mbarrier
+constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16 + 32 * kCoopStride * sizeof(double);  // + the mbarrier + one cooperative-tail strip per warp
 // The replicated table (+ the colour table right behind it) is prepared once per plane cost in global
 // memory (PcDev::lut_rep) and brought into shared memory by ONE TMA bulk copy (cp.async.bulk, SASS
 // UBLKCP) issued by thread 0 and tracked by an mbarrier; the other threads meanwhile draw their

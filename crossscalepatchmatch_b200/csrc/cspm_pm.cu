@@ -762,6 +762,18 @@ int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const doub
   });
 }
 
+int cspm_debug_lane_hist(unsigned long long* out33, int reset) {
+  return guard([&] {
+    CSPM_REQUIRE(out33, "null argument");
+    CSPM_CUDA(cudaDeviceSynchronize());
+    CSPM_CUDA(cudaMemcpyFromSymbol(out33, g_lane_hist, sizeof(unsigned long long) * 33));
+    if (reset) {
+      unsigned long long z[33] = {};
+      CSPM_CUDA(cudaMemcpyToSymbol(g_lane_hist, z, sizeof z));
+    }
+  });
+}
+
 int cspm_debug_counters(unsigned long long* out8, int reset) {
   return guard([&] {
     CSPM_REQUIRE(out8, "null argument");

@@ -185,6 +185,9 @@ int cspm_pm_stage_ms(const cspm_pm_t* pm, float* ms);
  * {task setup, per-scale prep, chunk pipeline, accept, grid barrier, -, -, -}
  * on the current device since the last reset; out8[8]. */
 int cspm_debug_counters(unsigned long long* out8, int reset);
+/* Diagnostic builds (-DCSPM_PROFILE_LANES=1) only, zeros otherwise: out33[k] = window rows the bulk kernels
+ * executed with k of a warp's 32 lanes still evaluating (per-lane early termination leaves the others idle). */
+int cspm_debug_lane_hist(unsigned long long* out33, int reset);
 
 #ifdef __cplusplus
 }
