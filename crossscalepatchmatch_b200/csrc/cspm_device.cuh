@@ -20,7 +20,7 @@
 #define CSPM_PROFILE_LANES 0
 #endif
 #ifndef CSPM_COOP_LANES
-#define CSPM_COOP_LANES 6
+#define CSPM_COOP_LANES 8
 #endif
 #ifndef CSPM_TAP_UNROLL
 #define CSPM_TAP_UNROLL 5
@@ -410,13 +410,16 @@ __device__ unsigned long long g_lane_hist[33];  // CSPM_PROFILE_LANES: window ro
 // Cooperative tail (single-scale bulk kernels, coop != nullptr).  Early termination is per lane, so a warp often ends up
 // with a handful of lanes still evaluating while the others idle (HD refinement: 15 % of all executed window
 // rows run with <= 4 of 32 lanes, profiles/r01_lane_hist.txt).  Once at most kCoopLanes lanes of a FULL warp are
-// left, the warp changes shape: for each surviving lane L in turn, all 32 lanes compute the <= 35 addends of
-// L's current window row — lane j takes tap x0_L + j, a second pass the last three — park them in a per-warp
-// shared-memory strip, and lane L alone adds them to its running sum in tap order.  The sum is formed by the
+// left, the warp changes shape: all 32 lanes compute the <= 35 addends of the survivors' current window rows
+// (four survivors at a time, their taps laid end to end and dealt to the lanes), park them in a per-warp
+// shared-memory strip, and each surviving lane adds its own row to its running sum in tap order.  The sum is formed by the
 // same operations in the same order as in the per-lane loop (bit-identical) and the per-row termination test is
-// unchanged.  Measured at HD: refinement 337 -> 328 ms with the switch at <= 6 lanes (2 / 4 / 8: 341 / 334 / 330).
+// unchanged.  Measured at HD: refinement 337 -> 316 ms with the switch at <= 8 lanes (6 / 12 / 16: 320 / 316 / 323;
+// one survivor at a time instead of groups of four: 328).
 constexpr int kCoopLanes = CSPM_COOP_LANES;  // switch to the cooperative tail at <= this many live lanes; 0: never
-constexpr int kCoopStride = 64;               // doubles per warp strip (a window row has at most 63 addends)
+constexpr int kCoopGroup = 4;                 // survivors handled together
+constexpr int kCoopSlot = 36;                 // doubles per survivor (windows up to 35 wide; larger ones skip the tail)
+constexpr int kCoopStride = kCoopGroup * kCoopSlot;  // doubles per warp strip
 template <int CC, int LWS, int CSM, int DIR, bool ALLVALID = false>
 __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& sc, const TapCtx& t, uint32_t Ip, int x0, int x1,
                                               int y0, int y1, double a, double b, double c, double bound, double cost_prev,
@@ -462,29 +465,45 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
     }
     const unsigned int alive = __ballot_sync(mask, !done);
     if (alive == 0u) return cost;
-    if (mask == 0xffffffffu && __popc(alive) <= kCoopLanes) { ++qy; break; }
+    if (mask == 0xffffffffu && __popc(alive) <= kCoopLanes && 2 * pc.half_wnd + 1 <= 35) { ++qy; break; }
   }
-  // ---- cooperative tail: rows qy .. y1 of the surviving lanes, one lane-row at a time
+  // ---- cooperative tail: rows qy .. y1 of the surviving lanes, kCoopGroup survivors at a time.  The taps of the
+  // group's rows are laid end to end (survivor k, tap j <-> index k * wnd + j) and dealt to the 32 lanes pass by
+  // pass, so a group of 4 needs 5 passes for its 140 taps; then the owners add their own rows side by side.
+  const int wnd = 2 * pc.half_wnd + 1;
+  const int my_n = x1 - x0 + 1;
   for (; qy <= y1; ++qy) {
     unsigned int todo = __ballot_sync(mask, !done);
     if (todo == 0u) break;
     const int row_off = qy * sc.pitch + sc.pad;
     const double my_qdy = dadd(dmul(b, (double)qy), c);
     while (todo) {
-      const int L = __ffs(todo) - 1;
-      todo &= todo - 1u;
-      const double aL = __shfl_sync(mask, a, L), qdyL = __shfl_sync(mask, my_qdy, L);
-      const uint32_t IpL = __shfl_sync(mask, Ip, L);
-      const int x0L = __shfl_sync(mask, x0, L), nL = __shfl_sync(mask, x1, L) - x0L + 1;
+      int src_lane[kCoopGroup];
+      unsigned int grp = 0u;
+      int gsz = 0;
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int j = lane + 32 * pass;
-        if (j < nL) coop[j] = tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, x0L + j, IpL, aL, qdyL);
+      for (int g = 0; g < kCoopGroup; ++g) {
+        src_lane[g] = todo ? __ffs(todo) - 1 : 0;
+        if (todo) { grp |= todo & (0u - todo); todo &= todo - 1u; ++gsz; }
+      }
+      const int ntap = gsz * wnd;
+      for (int base = 0; base < ntap; base += 32) {
+        const int idx = base + lane;
+        const bool act = idx < ntap;
+        const int k = act ? (wnd == 35 ? idx / 35 : idx / wnd) : 0;
+        const int j = idx - k * wnd;
+        int src = src_lane[0];
+#pragma unroll
+        for (int g = 1; g < kCoopGroup; ++g) src = k == g ? src_lane[g] : src;
+        const double aL = __shfl_sync(mask, a, src), qdyL = __shfl_sync(mask, my_qdy, src);
+        const uint32_t IpL = __shfl_sync(mask, Ip, src);
+        const int x0L = __shfl_sync(mask, x0, src), nL = __shfl_sync(mask, my_n, src);
+        if (act && j < nL) coop[k * kCoopSlot + j] = tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, x0L + j, IpL, aL, qdyL);
       }
       __syncwarp(mask);
-      if (lane == L) {
-        const volatile double* cp = coop;
-        for (int j = 0; j < nL; ++j) cost = dadd(cost, cp[j]);
+      if ((grp >> lane) & 1u) {
+        const volatile double* cp = coop + __popc(grp & ((1u << lane) - 1u)) * kCoopSlot;
+        for (int jj = 0; jj < my_n; ++jj) cost = dadd(cost, cp[jj]);
         const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
         if (total >= bound) done = true;
       }
@@ -565,7 +584,9 @@ __device__ __forceinline__ void stage_luts(const PcDev& pc, double* s_lut_w, dou
 constexpr int kLutWUsed = 766;
 constexpr int kLutRepShift = 4;
 constexpr size_t kBulkLutBytes = sizeof(double) * ((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);  // 98 304 B, multiple of 16
-constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16 + 32 * kCoopStride * sizeof(double);  // + the mbarrier + one cooperative-tail strip per warp
+constexpr int kBulkWarpsMax = CSPM_BULK_BY > CSPM_BULK_BY_CS ? CSPM_BULK_BY : CSPM_BULK_BY_CS;
+// + the mbarrier + one cooperative-tail strip per warp (126 KB with 24 warps: still the 132 KB carve-out)
+constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16 + (size_t)kBulkWarpsMax * kCoopStride * sizeof(double);
 // The replicated table (+ the colour table right behind it) is prepared once per plane cost in global
 // memory (PcDev::lut_rep) and brought into shared memory by ONE TMA bulk copy (cp.async.bulk, SASS
 // UBLKCP) issued by thread 0 and tracked by an mbarrier; the other threads meanwhile draw their
