@@ -9,3 +9,5 @@ python bench.py --config C1 --no-cpu-baseline > gpurun_out/cfg_C1_gpu.json 2>> g
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches.csv python profiles/run_one_step.py > /dev/null 2>&1
 head -c 300 gpurun_out/bench_final.json; echo
 for c in C1 C4cs; do python -c "import json;d=json.load(open('gpurun_out/cfg_${c}_gpu.json'));print('$c',round(d['value'],1),round(d['ms_per_step'],1),d['roofline']['frac'])"; done
+ncu --set full --clock-control none --import-source on -k regex:k_refine -s 1 -c 1 -o gpurun_out/final_refine -f python profiles/run_one_step.py > /dev/null 2>&1
+ls -la gpurun_out/final_refine.ncu-rep
