@@ -19,6 +19,9 @@
 #ifndef CSPM_PROFILE_LANES
 #define CSPM_PROFILE_LANES 0
 #endif
+#ifndef CSPM_COOP_CS
+#define CSPM_COOP_CS 0
+#endif
 #ifndef CSPM_COOP_LANES
 #define CSPM_COOP_LANES 8
 #endif
@@ -426,7 +429,8 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
                                               double w_s, double* coop = nullptr) {
   const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
   double cost = 0.0;
-  if (kCoopLanes == 0 || CSM != 0 || CC != CC_GRD || coop == nullptr) {  // (cross-scale: measured 1 % slower with the tail)
+  // (cross-scale: the first, ungrouped version of the tail was 1 % slower there — CSPM_COOP_CS=1 re-enables it for a re-measurement)
+  if (kCoopLanes == 0 || CSM < 0 || (CSM != 0 && !CSPM_COOP_CS) || CC != CC_GRD || coop == nullptr) {
     for (int qy = y0; qy <= y1; ++qy) {
       const double q_disp_y = dadd(dmul(b, (double)qy), c);
       const int row_off = qy * sc.pitch + sc.pad;
