@@ -429,7 +429,8 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
                                               double w_s, double* coop = nullptr) {
   const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
   double cost = 0.0;
-  // (cross-scale: the first, ungrouped version of the tail was 1 % slower there — CSPM_COOP_CS=1 re-enables it for a re-measurement)
+  // (cross-scale: the tail is a small loss there — C3 refinement 200 vs 196 ms with the grouped version, HD S=3 1 % with the
+  // ungrouped one: the deeper scales run with partial warps, and the extra live state spills; CSPM_COOP_CS=1 re-enables it)
   if (kCoopLanes == 0 || CSM < 0 || (CSM != 0 && !CSPM_COOP_CS) || CC != CC_GRD || coop == nullptr) {
     for (int qy = y0; qy <= y1; ++qy) {
       const double q_disp_y = dadd(dmul(b, (double)qy), c);
