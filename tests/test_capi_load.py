@@ -62,3 +62,22 @@ def test_argument_validation_without_gpu():
     assert c.GetCCType("CG") is None and c.GetCCType("nope") is None  # main.cc:47-54
     with pytest.raises(c.CspmError):
         c.PreSSPC(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8), 4, 35, c.GetCCType("GRD"))
+
+
+def test_headers_compile_as_c_and_cpp(tmp_path):
+    """include/cspm_c.h must be plain C (the boundary is a C ABI); include/cspm.hpp is self-contained C++17."""
+    import shutil
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    c_src = tmp_path / "t.c"
+    c_src.write_text('#include "cspm_c.h"\nint main(void) { return cspm_device_count() < 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(c_src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp_src = tmp_path / "t.cc"
+    cpp_src.write_text('#include "cspm.hpp"\nint main() { cspm::Plane p; (void)p; return 0; }\n')
+    r = subprocess.run([gxx, "-std=c++17", "-Wall", "-fsyntax-only", "-I", inc, str(cpp_src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
