@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSPM_LIB_PATH: load an alternative build of the same ABI (kernel-variant experiments)
 LIB_PATH = os.environ.get("CSPM_LIB_PATH") or os.path.join(_HERE, "libcspm_b200.so")
 
-OK, EINVAL, ENODEV, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
+OK, EINVAL, ENODEV, ENOMEM, EUNSUPPORTED, ECUDA = 0, -1, -2, -3, -4, -5
 SCHEDULE_RASTER, SCHEDULE_REDBLACK = 0, 1
 STAGE_INIT, STAGE_SPATIAL, STAGE_VIEW, STAGE_REFINE, STAGE_PLANE2DISP, STAGE_POSTPROC = range(6)
 
@@ -26,7 +26,9 @@ class CspmError(RuntimeError):
 
 
 class Stats(C.Structure):
-    _fields_ = [("kernel_launches", C.c_uint64), ("plane_evals", C.c_uint64), ("window_taps", C.c_uint64)]
+    _fields_ = [("kernel_launches", C.c_uint64), ("plane_evals", C.c_uint64), ("window_taps", C.c_uint64),
+                ("spatial_tasks", C.c_uint64), ("spatial_candidates", C.c_uint64), ("spatial_adopted", C.c_uint64),
+                ("spatial_exact_tasks", C.c_uint64)]
 
 
 _dp, _ip, _u8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
@@ -34,6 +36,8 @@ _dp, _ip, _u8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_u
 # name -> (restype, argtypes); exactly the symbols include/cspm_c.h declares
 SIGNATURES = {
     "cspm_last_error": (C.c_char_p, []),
+    "cspm_last_error_code": (C.c_int, []),
+    "cspm_debug_taps_executed": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "cspm_device_count": (C.c_int, []),
     "cspm_version": (C.c_char_p, []),
     "cspm_set_thread_stream": (None, [C.c_void_p]),
@@ -85,6 +89,11 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 def last_error() -> str:
     return (dll.cspm_last_error() or b"").decode()
+
+
+def raise_last():
+    """A creator returned NULL: raise with the code the library recorded for this thread."""
+    raise CspmError(dll.cspm_last_error_code() or EINVAL, last_error())
 
 
 def check(rc: int) -> int:

@@ -160,7 +160,7 @@ class IPlaneCost:
     def stats(self):
         s = _lib.Stats()
         check(dll.cspm_pc_stats(self._h, C.byref(s)))
-        return {"kernel_launches": s.kernel_launches, "plane_evals": s.plane_evals, "window_taps": s.window_taps}
+        return {name: getattr(s, name) for name, _ in _lib.Stats._fields_}
 
 
 def _ptr_and_geom(img, device_ptr):
@@ -184,7 +184,7 @@ class PreSSPC(IPlaneCost):
         fn = dll.cspm_pc_create_ss_dev if device_ptrs else dll.cspm_pc_create_ss
         self._h = fn(lp, rp, w, h, stride, max_disp, wnd_size, cc_method._h, device)
         if not self._h:
-            raise CspmError(_lib.ENODEV, _lib.last_error())
+            _lib.raise_last()
 
 
 class PreCSPC(IPlaneCost):
@@ -201,7 +201,7 @@ class PreCSPC(IPlaneCost):
         fn = dll.cspm_pc_create_cs_dev if device_ptrs else dll.cspm_pc_create_cs
         self._h = fn(lp, rp, w, h, stride, max_disp, wnd_size, scale_num, cc_method._h, float(reg_lambda), device)
         if not self._h:
-            raise CspmError(_lib.ENODEV, _lib.last_error())
+            _lib.raise_last()
 
 
 class GrdPC(IPlaneCost):
@@ -214,7 +214,7 @@ class GrdPC(IPlaneCost):
         self._h = dll.cspm_pc_create_grdpc(C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data), l.shape[1], l.shape[0],
                                            l.strides[0], max_disp, wnd_size, device)
         if not self._h:
-            raise CspmError(_lib.ENODEV, _lib.last_error())
+            _lib.raise_last()
 
 
 class CSPC(IPlaneCost):
@@ -227,7 +227,7 @@ class CSPC(IPlaneCost):
         self._h = dll.cspm_pc_create_cspc(C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data), l.shape[1], l.shape[0],
                                           l.strides[0], max_disp, wnd_size, scale_num, float(reg_lambda), device)
         if not self._h:
-            raise CspmError(_lib.ENODEV, _lib.last_error())
+            _lib.raise_last()
 
 
 class CSPatchMatch:
@@ -243,7 +243,7 @@ class CSPatchMatch:
         fn = dll.cspm_pm_create_dev if device_ptrs else dll.cspm_pm_create
         self._h = fn(lp, rp, w, h, stride, max_dis, dis_scale, seed, schedule, device)
         if not self._h:
-            raise CspmError(_lib.ENODEV, _lib.last_error())
+            _lib.raise_last()
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -286,7 +286,7 @@ class CSPatchMatch:
     def stats(self):
         s = _lib.Stats()
         check(dll.cspm_pm_stats(self._h, C.byref(s)))
-        return {"kernel_launches": s.kernel_launches, "plane_evals": s.plane_evals, "window_taps": s.window_taps}
+        return {name: getattr(s, name) for name, _ in _lib.Stats._fields_}
 
     def stage_ms(self):
         ms = (C.c_float * 6)()

@@ -22,6 +22,11 @@
 #ifndef CSPM_COOP_CS
 #define CSPM_COOP_CS 0
 #endif
+// -DCSPM_SP_PROFILE=1: cycle accounting inside the ring sweep (clock64 + global counters on the critical path of
+// CTA 0); compiled out of the default build.
+#ifndef CSPM_SP_PROFILE
+#define CSPM_SP_PROFILE 0
+#endif
 #ifndef CSPM_COOP_LANES
 #define CSPM_COOP_LANES 8
 #endif
@@ -68,6 +73,9 @@ struct PcDev {
   int cross_scale;             // 0: PreSSPC, 1: PreCSPC
   int scale_num;               // 1 for PreSSPC
   int half_wnd;                // wnd_size / 2
+  int monotone;                // 1: every scale weight is >= 0, so running sums never decrease (exact early termination
+                               // and the certified comparisons of the wavefront sweep rely on it); 0 (reg_lambda < 0
+                               // can give negative weights): every cost is summed in full
   ScaleDev sc[kMaxScales];
   double scale_wgt[kMaxScales];
   const double* lut_w;         // [kLutW]
@@ -397,6 +405,22 @@ __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, co
 }
 
 __device__ unsigned long long g_lane_hist[33];  // CSPM_PROFILE_LANES: window rows executed with k active lanes
+// -DCSPM_COUNT_TAPS=1: diagnostic build that counts the window taps the bulk kernels actually execute (per-lane
+// early termination skips the rest); read back with cspm_debug_taps_executed.  Never the benchmarked build.
+#ifndef CSPM_COUNT_TAPS
+#define CSPM_COUNT_TAPS 0
+#endif
+__device__ unsigned long long g_taps_exec;
+#if CSPM_COUNT_TAPS
+#define CSPM_TAPCOUNT(nn)                                                                     \
+  do {                                                                                        \
+    const unsigned int m__ = __activemask();                                                  \
+    const unsigned int t__ = __reduce_add_sync(m__, (unsigned int)(nn));                      \
+    if ((int)(threadIdx.x & 31) == __ffs(m__) - 1) atomicAdd(&g_taps_exec, (unsigned long long)t__); \
+  } while (0)
+#else
+#define CSPM_TAPCOUNT(nn) do { } while (0)
+#endif
 
 // PreSSPC::GetPlaneCost window at one scale, literal row-major accumulation
 // order (pre_ss_pc.cc:84-116 / pre_cs_pc.cc:151-181).
@@ -443,6 +467,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
 #endif
       CSPM_UNROLL(CSPM_TAP_UNROLL)  // independent taps in flight per thread (35 = 7 x 5); 24 warps per SM x 5 taps measured best
       for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
+      CSPM_TAPCOUNT(x1 - x0 + 1);
       const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
       if (total >= bound) break;
     }
@@ -465,6 +490,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
       const int row_off = qy * sc.pitch + sc.pad;
       CSPM_UNROLL(CSPM_TAP_UNROLL)
       for (int qx = x0; qx <= x1; ++qx) cost = dadd(cost, tap_term<CC, LWS, DIR, ALLVALID>(t, row_off, qx, Ip, a, q_disp_y));
+      CSPM_TAPCOUNT(x1 - x0 + 1);
       const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
       if (total >= bound) done = true;
     }
@@ -509,6 +535,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
       if ((grp >> lane) & 1u) {
         const volatile double* cp = coop + __popc(grp & ((1u << lane) - 1u)) * kCoopSlot;
         for (int jj = 0; jj < my_n; ++jj) cost = dadd(cost, cp[jj]);
+        CSPM_TAPCOUNT(my_n);
         const double total = cross ? dadd(cost_prev, dmul(cost, w_s)) : cost;
         if (total >= bound) done = true;
       }
@@ -517,7 +544,8 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
   }
   return cost;
 }
-template <int CC, int LWS = 0, int CSM = -1>
+// COOP = false: never take the cooperative tail (callers whose lanes do not share one image row).
+template <int CC, int LWS = 0, int CSM = -1, bool COOP = true>
 __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int rx, int ry, double a, double b,
                                               double c, const double* lut_w, const double* lut_c, double bound,
                                               double cost_prev, double w_s) {
@@ -542,7 +570,7 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
     }
     const bool all_ok = __all_sync(__activemask(), ok);
     // per-warp strip for the cooperative tail: behind the colour table and the mbarrier of the bulk layout
-    double* coop = const_cast<double*>(lut_c) + kLutC + 2 + (size_t)threadIdx.y * kCoopStride;
+    double* coop = COOP ? const_cast<double*>(lut_c) + kLutC + 2 + (size_t)threadIdx.y * kCoopStride : nullptr;
     if (all_ok)
       return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
                     : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
@@ -555,18 +583,20 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
 // IPlaneCost::GetPlaneCost: PreSSPC (pre_ss_pc.cc:74-118) or PreCSPC
 // (pre_cs_pc.cc:133-188).  Returns the exact cost if it is < bound, otherwise
 // some value >= bound (see window_cost).
-template <int CC, int LWS = 0, int CSM = -1>
+template <int CC, int LWS = 0, int CSM = -1, bool COOP = true>
 __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int ry, const PlaneD& p,
                                              const double* lut_w, const double* lut_c, double bound) {
+  // (bound is a by-value copy: callers keep comparing against their own)
   const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
-  if (!cross) return window_cost<CC, LWS, CSM>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
+  if (cross && !pc.monotone) bound = __longlong_as_double(0x7ff0000000000000ll);  // negative scale weights: no early termination
+  if (!cross) return window_cost<CC, LWS, CSM, COOP>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);
   int cx = rx, cy = ry;
   for (int s = 0; s < pc.scale_num; ++s) {
     PlaneD q = p;
     update_param(q, (double)cx, (double)cy, cur_disp);
-    const double sc_cost = window_cost<CC, LWS, CSM>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
+    const double sc_cost = window_cost<CC, LWS, CSM, COOP>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s]);
     cost = dadd(cost, dmul(sc_cost, pc.scale_wgt[s]));
     if (cost >= bound) break;
     cy /= 2;
@@ -739,10 +769,14 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
     const double* grd1 = sc.grad[1];
     const uint32_t* hi0 = sc.cen_hi[0];
     const uint32_t* hi1 = sc.cen_hi[1];
+#if CSPM_SP_PROFILE
     const bool prof = blockIdx.x == gridDim.x / 2 && lane == 0;
     const long long loop_t0 = clock64();
+#endif
     for (int ci = 0; ci <= nchunks; ++ci) {
+#if CSPM_SP_PROFILE
       const long long it_t0 = clock64();
+#endif
       if (!consumer) {
         if (ci < nchunks) {  // produce chunk ci (whole window rows)
           const int dy0 = ci * chunk_rows, len = min(chunk_rows, wnd - dy0) * wnd;
@@ -814,11 +848,15 @@ __device__ __forceinline__ double engine_eval_pairs(const PcDev& pc, const Engin
           if (f != pd[lane >> 1].flags) pd[lane >> 1].flags = f;
         }
       }
+#if CSPM_SP_PROFILE
       if (prof && consumer) g_eng_prof[0] += (unsigned long long)(clock64() - it_t0);
       if (prof && warp == 0) g_eng_prof[1] += (unsigned long long)(clock64() - it_t0);
+#endif
       __syncthreads();
     }
+#if CSPM_SP_PROFILE
     if (prof && warp == 0) g_eng_prof[2] += (unsigned long long)(clock64() - loop_t0);
+#endif
     if (consumer && ch_on) {
       if (pc.cross_scale) cost = dadd(cost, dmul(sum, pc.scale_wgt[s]));  // pre_cs_pc.cc:182
       else cost = sum;

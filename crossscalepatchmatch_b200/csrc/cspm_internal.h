@@ -19,13 +19,15 @@ struct Error : std::runtime_error {
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-void set_last_error(const std::string& msg);
+void set_last_error(const std::string& msg, int code = CSPM_EINVAL);
 
 #define CSPM_CUDA(call)                                                                          \
   do {                                                                                           \
     cudaError_t e__ = (call);                                                                    \
     if (e__ != cudaSuccess)                                                                      \
-      throw ::cspm::Error(e__ == cudaErrorMemoryAllocation ? CSPM_ENOMEM : CSPM_ENODEV,          \
+      throw ::cspm::Error(e__ == cudaErrorMemoryAllocation ? CSPM_ENOMEM                         \
+                          : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ||  \
+                             e__ == cudaErrorInvalidDevice) ? CSPM_ENODEV : CSPM_ECUDA,          \
                           std::string(#call) + ": " + cudaGetErrorString(e__));                  \
   } while (0)
 
@@ -41,21 +43,22 @@ int guard(F&& f) {
     f();
     return CSPM_OK;
   } catch (const Error& e) {
-    set_last_error(e.what());
+    set_last_error(e.what(), e.code);
     return e.code;
+  } catch (const std::bad_alloc& e) {
+    set_last_error(e.what(), CSPM_ENOMEM);
+    return CSPM_ENOMEM;
   } catch (const std::exception& e) {
-    set_last_error(e.what());
-    return CSPM_ENODEV;
+    set_last_error(e.what(), CSPM_ECUDA);
+    return CSPM_ECUDA;
   }
 }
+// Creators return NULL; the reason stays readable through cspm_last_error() / cspm_last_error_code().
 template <typename T, typename F>
 T* guard_ptr(F&& f) {
-  try {
-    return f();
-  } catch (const std::exception& e) {
-    set_last_error(e.what());
-    return nullptr;
-  }
+  T* out = nullptr;
+  guard([&] { out = f(); });
+  return out;
 }
 
 // Selects the device for the current thread and checks it exists.  This is
@@ -144,7 +147,13 @@ struct cspm_pm {
   unsigned long long* tmin = nullptr;
   unsigned int* win = nullptr;
   unsigned long long* tap_counter = nullptr;
-  unsigned int* grid_barrier = nullptr;  // persistent spatial sweep
+  unsigned int* grid_barrier = nullptr;  // persistent spatial sweep: one progress word (own 128-B line) per CTA
+  // wavefront sweep (cspm_pm_wave.cuh): pixels that adopted a plane on the fast path, their compacted lists,
+  // list lengths [2] and the sweep counters
+  uint8_t* wave_changed = nullptr;       // [2][w*h]
+  int* wave_list = nullptr;              // [2][w*h]
+  unsigned int* wave_count = nullptr;    // [2]
+  unsigned long long* wave_stats = nullptr;  // [4], accumulated over the sweeps of a call
   // post-processing scratch
   int* valid[2] = {nullptr, nullptr};
   uint8_t* dis_tmp = nullptr;

@@ -206,11 +206,17 @@ __global__ void __launch_bounds__(128) k_spatial_diag(PcDev pc, PmDev pm, int di
 // `<`, :270); the original plane wins ties.  Parallel form: evaluate all
 // proposals, atomicMin the cost bits per target, then atomicMin the scan
 // position among the proposals that hit the minimum, then the winner writes.
+// f64 -> u64, order-preserving for every finite value and the infinities (costs can be negative when reg_lambda < 0
+// makes a scale weight negative): atomicMin on the keys is the minimum of the costs.
+__device__ __forceinline__ unsigned long long cost_key(double c) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
 __global__ void k_view_begin(PmDev pm, int v, unsigned long long* tmin, unsigned int* win) {
   const size_t n = (size_t)pm.w * pm.h;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  tmin[i] = (unsigned long long)__double_as_longlong(pm.st[v][6 * n + i]);
+  tmin[i] = cost_key(pm.st[v][6 * n + i]);
   win[i] = 0xFFFFFFFFu;
 }
 __device__ __forceinline__ void view_candidate(const PmDev& pm, int v, int x, int y, PlaneD* q, int* cor_x) {
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_view_eval(PcD
     const size_t i = (size_t)y * pm.w + x;
     cand_cost[i] = cost;
     cand_tx[i] = cor_x;
-    atomicMin(&tmin[(size_t)y * pm.w + cor_x], (unsigned long long)__double_as_longlong(cost));
+    atomicMin(&tmin[(size_t)y * pm.w + cor_x], cost_key(cost));
     int cx = cor_x, cy = y;
     for (int s = 0; s < pc.scale_num; ++s) {
       const ScaleDev& sc = pc.sc[s];
@@ -266,7 +272,7 @@ __global__ void k_view_resolve(PmDev pm, int v, int rev, const double* cand_cost
   const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
   const size_t t = (size_t)y * pm.w + cand_tx[i];
   const double cost = cand_cost[i];
-  if ((unsigned long long)__double_as_longlong(cost) == tmin[t] && cost < pm.st[v][6 * n + t])
+  if (cost_key(cost) == tmin[t] && cost < pm.st[v][6 * n + t])
     atomicMin(&win[t], (unsigned int)(rev ? pm.w - 1 - x : x));
 }
 __global__ void k_view_commit(PmDev pm, int v, int rev, const double* cand_cost, const int* cand_tx,
@@ -284,6 +290,7 @@ __global__ void k_view_commit(PmDev pm, int v, int rev, const double* cand_cost,
 }
 
 #include "cspm_pm_engine.cuh"
+#include "cspm_pm_wave.cuh"
 
 // -------------------------------------------------------------- plane2disp
 __global__ void k_plane2disp(PmDev pm, uint8_t* dis0, uint8_t* dis1) {
@@ -460,6 +467,23 @@ static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
   pm->stats.window_taps += 2ull * pm->n_ref * pc->taps_per_image_eval;
 }
 
+// Which sweep implementation: "wave" (default: parallel sums + certified comparisons + exact cost fix-up,
+// cspm_pm_wave.cuh), "ring" (round 1: streaming evaluator with one serial add chain per candidate,
+// cspm_pm_engine.cuh) or "diag" (one launch per anti-diagonal).  All three are bit-identical; the environment
+// variable CSPM_SPATIAL exists for A/B measurements and for the tests that cross-check them.
+enum SpatialMode { SP_WAVE = 0, SP_RING = 1, SP_DIAG = 2 };
+static SpatialMode spatial_mode() {
+  const char* e = getenv("CSPM_SPATIAL");
+  if (!e) return SP_WAVE;
+  const std::string m(e);
+  return m == "diag" ? SP_DIAG : m == "ring" ? SP_RING : SP_WAVE;
+}
+// CSPM_SP_CTAS=n caps the persistent grid (tests: several pixels per CTA and multi-pass diagonals on small images)
+static int spatial_cta_cap() {
+  const char* e = getenv("CSPM_SP_CTAS");
+  return e ? std::max(1, atoi(e)) : 0;
+}
+
 static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   const int rev = (iter % 2 == 0) ? 0 : 1;
   const int wnd = 2 * pc->dev.half_wnd + 1;
@@ -467,38 +491,74 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   PmDev d = pm_dev(pm);
   d.cost_consistent = pm->cost_owner == pc->uid;
   PcDev pcd = pc->dev;
-  static const bool force_diag = [] {
-    const char* e = getenv("CSPM_SPATIAL");
-    return e && std::string(e) == "diag";
-  }();
-  bool persistent = !force_diag;
-  const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
+  SpatialMode mode = spatial_mode();
+  const size_t n = (size_t)pm->w * pm->h;
   int sms = 0, coop = 0, occ = 0;
-  void (*kern)(PcDev, PmDev, int, unsigned int*) = nullptr;
-  CSPM_DISPATCH_CC(pcd.cc_kind, kern = wnd == 35 ? k_spatial_persist<CC, 35> : k_spatial_persist<CC, 0>);
-  if (persistent) {
+  if (mode != SP_DIAG) {
     CSPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pm->device));
     CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm->device));
-    CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSpThreads, smem_p));
-    persistent = coop && occ >= kSpCtasPerSm;
+    if (!coop) mode = SP_DIAG;
   }
-  if (persistent) {
-    // one cooperative launch per sweep; the grid barrier needs every CTA resident
-    CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, pm->stream));
-    int rev_arg = rev;
-    unsigned int* bar = pm->grid_barrier;
-    void* args[] = {&pcd, &d, &rev_arg, &bar};
-    const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(sms * kSpCtasPerSm), dim3(kSpThreads), args, smem_p, pm->stream);
-    if (ce == cudaSuccess) {
-      pm->stats.kernel_launches++;
-    } else {  // e.g. SMs partly taken by another context: fall back to one launch per diagonal (same results)
-      cudaGetLastError();
-      persistent = false;
+  const int cap = spatial_cta_cap();
+  if (mode == SP_WAVE) {
+    void (*kern)(PcDev, PmDev, int, unsigned int*, uint8_t*, unsigned long long*, double, int) = nullptr;
+    CSPM_DISPATCH_CC(pcd.cc_kind, kern = k_spatial_wave<CC>);
+    CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWvSmemBytes));
+    CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWvThreads, kWvSmemBytes));
+    if (occ < 1) mode = SP_DIAG;
+    else {
+      // a CTA only helps while it has a pixel: never more CTAs than the longest diagonal has pixels
+      int grid = std::min(sms, std::min(pm->w, pm->h));
+      if (cap) grid = std::min(grid, cap);
+      CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, pm->stream));
+      CSPM_CUDA(cudaMemsetAsync(pm->wave_changed, 0, 2 * n, pm->stream));
+      CSPM_CUDA(cudaMemsetAsync(pm->wave_count, 0, 2 * sizeof(unsigned int), pm->stream));
+      // |row-major chain - tree sum| <= eps * tree sum for n non-negative addends (header of cspm_pm_wave.cuh)
+      double eps = 4.0 * (double)wnd * wnd * pcd.scale_num * 1.1102230246251565e-16;
+      static const bool env_exact = [] { const char* e = getenv("CSPM_WAVE_EXACT"); return e && atoi(e) != 0; }();
+      int force_exact = (env_exact || !pcd.monotone) ? 1 : 0;
+      int rev_arg = rev;
+      unsigned int* prog = pm->grid_barrier;
+      uint8_t* changed = pm->wave_changed;
+      unsigned long long* wst = pm->wave_stats;
+      void* args[] = {&pcd, &d, &rev_arg, &prog, &changed, &wst, &eps, &force_exact};
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kWvThreads), args, kWvSmemBytes, pm->stream);
+      if (ce != cudaSuccess) {  // e.g. SMs partly taken by another context: one launch per diagonal instead (same results)
+        cudaGetLastError();
+        mode = SP_DIAG;
+      } else {
+        k_wave_compact<<<dim3((unsigned)((n + 255) / 256), 2), 256, 0, pm->stream>>>(pm->wave_changed, (int)n, pm->wave_list, pm->wave_count);
+        CSPM_DISPATCH_CC_CS(pcd.cc_kind, pcd.cross_scale, constexpr int by = bulk_by<CS>(); bulk_smem(k_cost_fix<CC, CS>);
+                            k_cost_fix<CC, CS><<<dim3((unsigned)((n + 32 * by - 1) / (32 * by)), 2), dim3(32, by), kBulkSmemBytes, pm->stream>>>(
+                                pcd, d, pm->wave_list, pm->wave_count));
+        pm->stats.kernel_launches += 3;
+      }
     }
   }
-  if (!persistent) {
+  if (mode == SP_RING) {
+    const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
+    void (*kern)(PcDev, PmDev, int, unsigned int*) = nullptr;
+    CSPM_DISPATCH_CC(pcd.cc_kind, kern = wnd == 35 ? k_spatial_persist<CC, 35> : k_spatial_persist<CC, 0>);
+    CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSpThreads, smem_p));
+    if (occ < kSpCtasPerSm) mode = SP_DIAG;
+    else {
+      CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, pm->stream));
+      int rev_arg = rev;
+      unsigned int* bar = pm->grid_barrier;
+      void* args[] = {&pcd, &d, &rev_arg, &bar};
+      const int grid = cap ? std::min(cap, sms * kSpCtasPerSm) : sms * kSpCtasPerSm;
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kSpThreads), args, smem_p, pm->stream);
+      if (ce == cudaSuccess) pm->stats.kernel_launches++;
+      else {
+        cudaGetLastError();
+        mode = SP_DIAG;
+      }
+    }
+  }
+  if (mode == SP_DIAG) {
     const size_t smem = sizeof(double) * (kLutW + kLutC + 2 * (size_t)wnd * wnd);
+    CSPM_DISPATCH_CC(pcd.cc_kind, CSPM_CUDA(cudaFuncSetAttribute(k_spatial_diag<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     for (int diag = 1; diag <= pm->w + pm->h - 2; ++diag) {
       const int u_lo = std::max(0, diag - (pm->h - 1)), u_hi = std::min(diag, pm->w - 1);
       dim3 g(u_hi - u_lo + 1, 2);
@@ -561,8 +621,16 @@ static void sync_taps(cspm_pm* pm) {
   unsigned long long t = 0;
   CSPM_CUDA(cudaMemcpyAsync(&t, pm->tap_counter, sizeof(t), cudaMemcpyDeviceToHost, pm->stream));
   CSPM_CUDA(cudaStreamSynchronize(pm->stream));
+  unsigned long long ws[kWvStats] = {};
+  CSPM_CUDA(cudaMemcpyAsync(ws, pm->wave_stats, sizeof(ws), cudaMemcpyDeviceToHost, pm->stream));
+  CSPM_CUDA(cudaStreamSynchronize(pm->stream));
   pm->stats.window_taps += t;
+  pm->stats.spatial_tasks += ws[0];
+  pm->stats.spatial_candidates += ws[1];
+  pm->stats.spatial_adopted += ws[2];
+  pm->stats.spatial_exact_tasks += ws[3];
   CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(t), pm->stream));
+  CSPM_CUDA(cudaMemsetAsync(pm->wave_stats, 0, sizeof(ws), pm->stream));
 }
 
 }  // namespace cspm
@@ -613,6 +681,11 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
       pm->dis_tmp = pm->arena.alloc<uint8_t>(n);
       pm->tap_counter = pm->arena.alloc<unsigned long long>(1);
       pm->grid_barrier = pm->arena.alloc<unsigned int>(32 * 1024);  // one 128-B line per CTA
+      pm->wave_changed = pm->arena.alloc<uint8_t>(2 * n);
+      pm->wave_list = pm->arena.alloc<int>(2 * n);
+      pm->wave_count = pm->arena.alloc<unsigned int>(2);
+      pm->wave_stats = pm->arena.alloc<unsigned long long>(kWvStats);
+      CSPM_CUDA(cudaMemsetAsync(pm->wave_stats, 0, sizeof(unsigned long long) * kWvStats, pm->stream));
       CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(unsigned long long), pm->stream));
       CSPM_CUDA(cudaStreamSynchronize(pm->stream));
       return pm;
@@ -669,13 +742,17 @@ int cspm_pm_patchmatch(cspm_pm_t* pm, int iter_num, const cspm_pc_t* pc, int use
     CSPM_REQUIRE(iter_num >= 0, "negative iteration count");
     use_device(pm->device);
     // stage timing: events on the handle's stream
-    std::vector<cudaEvent_t> ev;
+    struct Events {  // destroyed on every exit path
+      std::vector<cudaEvent_t> v;
+      ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } evs;
+    std::vector<cudaEvent_t>& ev = evs.v;
     std::vector<int> ev_stage;
     auto mark = [&](int stage) {
       cudaEvent_t e;
       CSPM_CUDA(cudaEventCreate(&e));
-      CSPM_CUDA(cudaEventRecord(e, pm->stream));
       ev.push_back(e);
+      CSPM_CUDA(cudaEventRecord(e, pm->stream));
       ev_stage.push_back(stage);
     };
     mark(CSPM_STAGE_INIT);
@@ -703,7 +780,6 @@ int cspm_pm_patchmatch(cspm_pm_t* pm, int iter_num, const cspm_pc_t* pc, int use
       CSPM_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
       pm->stage_ms[ev_stage[k]] += ms;
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
   });
 }
 
@@ -759,6 +835,18 @@ int cspm_pm_set_planes(cspm_pm_t* pm, int view, const double* normal, const doub
     CSPM_CUDA(cudaMemcpyAsync(pm->st[view], h.data(), sizeof(double) * 7 * n, cudaMemcpyHostToDevice, pm->stream));
     CSPM_CUDA(cudaStreamSynchronize(pm->stream));
     pm->cost_owner = 0;  // caller-supplied costs: no longer known to be GetPlaneCost of the stored planes
+  });
+}
+
+int cspm_debug_taps_executed(unsigned long long* out, int reset) {
+  return guard([&] {
+    CSPM_REQUIRE(out, "null argument");
+    CSPM_CUDA(cudaDeviceSynchronize());
+    CSPM_CUDA(cudaMemcpyFromSymbol(out, g_taps_exec, sizeof(unsigned long long)));
+    if (reset) {
+      unsigned long long z = 0;
+      CSPM_CUDA(cudaMemcpyToSymbol(g_taps_exec, &z, sizeof z));
+    }
   });
 }
 

@@ -31,6 +31,7 @@ constexpr int kSpRows = 5;      // window rows per pipeline chunk (WND = 35)
 // Cycle accounting of the persistent sweep (CTA 0 only; read back through
 // cspm_debug_counters): {neighbour wait + task setup, evaluation, accept, publish}.
 __device__ unsigned long long g_sp_prof[8];
+#if CSPM_SP_PROFILE
 #define SP_PROF(slot)                                              \
   do {                                                             \
     if (blockIdx.x == 0 && threadIdx.x == 0) {                     \
@@ -39,6 +40,9 @@ __device__ unsigned long long g_sp_prof[8];
       prof_t = now__;                                              \
     }                                                              \
   } while (0)
+#else
+#define SP_PROF(slot) do { } while (0)
+#endif
 
 template <int CC, int WND>
 __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(PcDev pc, PmDev pm, int rev, unsigned int* barrier_ctr) {
@@ -50,7 +54,9 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
   const bool consumer = warp == kSpThreads / 32 - 1;
   const size_t n = (size_t)pm.w * pm.h;
   const int inc = rev ? -1 : 1;
+#if CSPM_SP_PROFILE
   long long prof_t = clock64();
+#endif
 
   for (int diag = 1; diag <= pm.w + pm.h - 2; ++diag) {
     const int u_lo = max(0, diag - (pm.h - 1)), u_hi = min(diag, pm.w - 1);
@@ -140,7 +146,8 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
       }
 #endif
       // both candidates must beat the pixel's cost at the start of the step (cs_patchmatch.cc:201,209)
-      const double ch_bound = __shfl_sync(0xffffffffu, ch_min, lane & ~1);
+      // (negative scale weights, reg_lambda < 0: sums are not monotone, no early termination)
+      const double ch_bound = pc.monotone ? __shfl_sync(0xffffffffu, ch_min, lane & ~1) : CUDART_INF;
       SP_PROF(0);
       const double ch_cost = WND == 35
           ? engine_eval_pairs_ring<CC, kSpThreads>(pc, rs, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound)

@@ -16,7 +16,11 @@
 namespace cspm {
 
 static thread_local std::string g_last_error;
-void set_last_error(const std::string& msg) { g_last_error = msg; }
+static thread_local int g_last_error_code = CSPM_OK;
+void set_last_error(const std::string& msg, int code) {
+  g_last_error = msg;
+  g_last_error_code = code;
+}
 
 static thread_local cudaStream_t g_thread_stream = nullptr;
 static thread_local bool g_thread_stream_set = false;
@@ -489,6 +493,11 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     if (cross_scale) scale_weights(scale_num, reg_lambda, &pc->scale_wgt);
     else pc->scale_wgt.assign(1, 1.0);
     for (int s = 0; s < pc->scale_num; ++s) D.scale_wgt[s] = pc->scale_wgt[s];
+    // reg_lambda < 0 (user-reachable, main.cc:34) can make a scale weight negative: window sums are then no longer
+    // monotone, so the kernels neither terminate early nor certify comparisons from partial sums
+    D.monotone = 1;
+    for (int s = 0; s < pc->scale_num; ++s)
+      if (!(pc->scale_wgt[s] >= 0.0)) D.monotone = 0;
 
     // in-image window taps of one evaluation at every pixel of scale 0
     // (the centre of scale s is (x>>s, y>>s), pre_cs_pc.cc:183-184)
@@ -524,6 +533,7 @@ using namespace cspm;
 extern "C" {
 
 const char* cspm_last_error(void) { return g_last_error.c_str(); }
+int cspm_last_error_code(void) { return g_last_error_code; }
 const char* cspm_version(void) { return "cspm-b200 0.1 (sm_100a)"; }
 int cspm_device_count(void) {
   int n = 0;

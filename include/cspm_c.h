@@ -41,9 +41,10 @@ extern "C" {
 
 #define CSPM_OK 0
 #define CSPM_EINVAL (-1)  /* bad argument (NULL, size, unknown name) */
-#define CSPM_ENODEV (-2)  /* no usable CUDA device / CUDA runtime error */
+#define CSPM_ENODEV (-2)  /* no usable CUDA device (there is no CPU fallback) */
 #define CSPM_ENOMEM (-3)
 #define CSPM_EUNSUPPORTED (-4)
+#define CSPM_ECUDA (-5)   /* any other CUDA runtime failure (launch, copy, ...); the message names the call */
 
 #define CSPM_VIEW_LEFT 0  /* RefView::kLeft,  commfunc.h:29 */
 #define CSPM_VIEW_RIGHT 1 /* RefView::kRight */
@@ -69,6 +70,9 @@ typedef struct cspm_pc cspm_pc_t; /* IPlaneCost    plane_cost/i_plane_cost.h:13-
 typedef struct cspm_pm cspm_pm_t; /* CSPatchMatch  cs_patchmatch.h:16-147 */
 
 const char* cspm_last_error(void);
+/* CSPM_E* code of the calling thread's last failed call (creators return NULL: this is how to tell EINVAL from
+ * ENODEV / ENOMEM / EUNSUPPORTED). */
+int cspm_last_error_code(void);
 /* Number of visible CUDA devices (0 when there is none); never fails. */
 int cspm_device_count(void);
 const char* cspm_version(void);
@@ -171,7 +175,13 @@ void* cspm_pm_stream(const cspm_pm_t* pm);
 typedef struct cspm_stats {
   uint64_t kernel_launches;
   uint64_t plane_evals;
-  uint64_t window_taps;
+  uint64_t window_taps; /* nominal: every in-image tap of every evaluation, whether or not early termination cut it */
+  /* SpatialPropagation sweeps (wavefront kernel): pixel tasks, candidate planes evaluated (after the exact
+   * duplicate shortcuts), planes adopted from certified comparisons, tasks that needed the exact serial path */
+  uint64_t spatial_tasks;
+  uint64_t spatial_candidates;
+  uint64_t spatial_adopted;
+  uint64_t spatial_exact_tasks;
 } cspm_stats_t;
 int cspm_pm_stats(const cspm_pm_t* pm, cspm_stats_t* out);
 int cspm_pc_stats(const cspm_pc_t* pc, cspm_stats_t* out);
@@ -185,6 +195,10 @@ int cspm_pm_stage_ms(const cspm_pm_t* pm, float* ms);
  * {task setup, per-scale prep, chunk pipeline, accept, grid barrier, -, -, -}
  * on the current device since the last reset; out8[8]. */
 int cspm_debug_counters(unsigned long long* out8, int reset);
+/* Diagnostic builds (-DCSPM_COUNT_TAPS=1) only, zero otherwise: window taps the bulk kernels (init, view,
+ * refinement, cost fix-up) actually EXECUTED on the current device since the last reset — the nominal count
+ * minus what exact early termination skipped. */
+int cspm_debug_taps_executed(unsigned long long* out, int reset);
 /* Diagnostic builds (-DCSPM_PROFILE_LANES=1) only, zeros otherwise: out33[k] = window rows the bulk kernels
  * executed with k of a warp's 32 lanes still evaluating (per-lane early termination leaves the others idle). */
 int cspm_debug_lane_hist(unsigned long long* out33, int reset);

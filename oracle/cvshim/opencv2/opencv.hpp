@@ -38,12 +38,29 @@
 #include "../../prims.h"
 
 // ---- deterministic stand-in for time(NULL) --------------------------------
+// mode 0: call counter — the RNG contract's stream id in a single-threaded run (parity, 1 thread)
+// mode 1: constant, like a real wall clock within one second (timing runs)
+// mode 2: the SAME stream ids as mode 0 with the reference's OpenMP row loops running in parallel.  Every
+//         `#pragma omp parallel for` over rows (cs_patchmatch.cc:126,305) makes exactly H calls, one per row, so
+//         the call count before a call, divided by H, is the index R of the loop it belongs to whatever the
+//         interleaving; libgomp's default static schedule gives thread t the contiguous rows starting at
+//         t*q + min(t, r) (q = H / nt, r = H % nt), in order, so row = start + (calls this thread made in loop R).
+//         tests/test_oracle_vs_ref.py checks mode 2 on 1..N threads == mode 0 bit for bit.
 inline uint64_t g_cspm_shim_seed = 0x5EED;
 inline std::atomic<uint64_t> g_cspm_shim_time_calls{0};
-inline int g_cspm_shim_time_mode = 0;  // 0: call counter (parity), 1: constant (like a real wall clock within one second)
+inline int g_cspm_shim_time_mode = 0;
+inline uint64_t g_cspm_shim_rows = 0;  // image height (mode 2), set by ref_pm_create
+inline uint64_t g_cspm_shim_epoch = 0;  // bumped whenever the wrapper rewinds the call counter
 inline uint64_t cspm_shim_time() {
   if (g_cspm_shim_time_mode == 1) return 1;
-  return g_cspm_shim_time_calls.fetch_add(1);
+  const uint64_t c = g_cspm_shim_time_calls.fetch_add(1);
+  if (g_cspm_shim_time_mode != 2 || !omp_in_parallel() || c == 0 || g_cspm_shim_rows == 0) return c;
+  const uint64_t H = g_cspm_shim_rows, R = (c - 1) / H;
+  static thread_local uint64_t loop = ~0ull, epoch = ~0ull, k = 0;
+  if (loop != R || epoch != g_cspm_shim_epoch) { loop = R; epoch = g_cspm_shim_epoch; k = 0; }
+  const uint64_t nt = (uint64_t)omp_get_num_threads(), t = (uint64_t)omp_get_thread_num();
+  const uint64_t q = H / nt, r = H % nt, start = t * q + (t < r ? t : r);
+  return 1 + R * H + start + k++;
 }
 #define time(x) cspm_shim_time()
 

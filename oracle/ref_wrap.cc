@@ -159,6 +159,7 @@ int ref_pc_scale_image(const void* p_, int s, int view, uint8_t* out) {
 void* ref_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride, int max_dis,
                     int dis_scale, uint64_t seed) {
   g_cspm_shim_seed = seed;
+  g_cspm_shim_rows = (uint64_t)h;
   g_cspm_shim_time_calls = 0;  // the ctor's time(NULL) is call 0 (cs_patchmatch.cc:32)
   Mat lm(h, w, CV_8UC3, (void*)l, (size_t)stride), rm(h, w, CV_8UC3, (void*)r, (size_t)stride);
   return new CSPatchMatch(lm, rm, max_dis, dis_scale);
@@ -169,6 +170,7 @@ void ref_pm_patchmatch(void* pm_, int iter_num, const void* pc_, int use_pp, int
   // time-mode 0 (call counter) is only deterministic single-threaded
   omp_set_num_threads(g_cspm_shim_time_mode == 0 ? 1 : (nthreads > 0 ? nthreads : omp_get_num_procs()));
   g_cspm_shim_time_calls = 1;
+  ++g_cspm_shim_epoch;
   Quiet q;
   pm->PatchMatch(iter_num, ((const RefPC*)pc_)->pc, use_pp != 0);
 }
@@ -178,6 +180,7 @@ void ref_pm_stage(void* pm_, int stage, int iter, const void* pc_, int nthreads)
   const IPlaneCost* pc = pc_ ? ((const RefPC*)pc_)->pc : NULL;
   omp_set_num_threads(g_cspm_shim_time_mode == 0 ? 1 : (nthreads > 0 ? nthreads : omp_get_num_procs()));
   const uint64_t H = pm->hei_;
+  ++g_cspm_shim_epoch;
   Quiet q;
   switch (stage) {
     case 0: g_cspm_shim_time_calls = 1; pm->InitRandomPlane(pc); break;

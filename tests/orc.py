@@ -196,3 +196,14 @@ def ref() -> Lib:
     if "ref" not in _libs:
         _libs["ref"] = Lib(os.path.join(ORACLE_DIR, "_ref", "libcspm_ref.so"), "ref_")
     return _libs["ref"]
+
+
+def ref_fast_available() -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libcspm_ref_fast.so"))
+
+
+def ref_fast() -> Lib:
+    """The same unmodified reference sources built -O3 -march=x86-64-v3 (timing build, oracle/Makefile)."""
+    if "ref_fast" not in _libs:
+        _libs["ref_fast"] = Lib(os.path.join(ORACLE_DIR, "_ref", "libcspm_ref_fast.so"), "ref_")
+    return _libs["ref_fast"]

@@ -1,7 +1,7 @@
-"""Full-size (BASELINE.json configs[3]: 1920x1080, max_dis=256) checks through the C ABI.  The oracle
-needs an 8.5 GB cost volume and ~20 CPU-minutes at this size, so here the result is pinned by
-size-independent properties instead: determinism, per-pixel monotone costs, disparity/plane
-consistency recomputed in numpy, evaluation counters, and ground-truth agreement."""
+"""Full-size (BASELINE.json configs[3]: 1920x1080, max_dis=256) checks through the C ABI: size-independent
+properties — determinism, per-pixel monotone costs, disparity/plane consistency recomputed in numpy,
+evaluation counters, ground-truth agreement.  (Parity with the reference's own code at this size is
+tests/test_gpu_configs.py, against fixtures generated from oracle/_ref.)"""
 import numpy as np
 import pytest
 
@@ -68,12 +68,7 @@ def test_hd_full_run_deterministic_and_accurate(cspm, hd):
         runs.append((pm.dis(0), pm.dis(1), pm.planes(0)[2]))
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
     assert np.array_equal(runs[0][2], runs[1][2]), "bit-identical costs run to run"
-    # Regression pin: every kernel version of round 1 — from the first one, whose stages were checked bit for bit
-    # against the oracle at the sizes the oracle can run, to the packed-layout / cooperative-tail kernels —
-    # produced exactly these two HD disparity maps (scratch/time_step.py prints the same digest).
-    import hashlib
-    digest = hashlib.sha1(runs[0][0].tobytes() + runs[0][1].tobytes()).hexdigest()
-    assert digest.startswith("fb7464215552"), f"HD disparity maps changed: sha1 {digest}"
+    # (the maps themselves are pinned against the reference's own code in tests/test_gpu_configs.py::C4)
     # sanity (not parity): agreement with the synthetic ground truth on the left view
     err = np.abs(runs[0][0].astype(np.float64) - np.minimum(gt, 255.0))
     frac = (err <= 1.0).mean()

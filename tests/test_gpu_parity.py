@@ -145,7 +145,7 @@ def test_image_interpolating_plane_costs(cspm, orc_lib, pair, S, lam):
         cspm.GrdPC(l[:, :16].copy(), r[:, :16].copy(), 17, 35)  # max_disp > width: out-of-row reads in the reference
 
 
-@pytest.mark.parametrize("wnd", [5, 11, 21, 41])
+@pytest.mark.parametrize("wnd", [5, 11, 21, 41, 63])
 def test_other_window_sizes(cspm, orc_lib, wnd):
     """wnd_size is a constructor argument of PreSSPC/PreCSPC (main.cc fixes 35): the generic-window
     code paths (runtime window size in every kernel, chunked pipeline in the spatial sweep)."""
@@ -248,6 +248,8 @@ def test_spatial_shortcuts_are_exact_on_foreign_state(cspm, orc_lib, pair, S, la
     (6, 1, 2, 1, 0, 0.0, 2, False),      # single row
     (2, 2, 1, 1, 0, 0.0, 1, False),
     (40, 33, 40, 1, 0, 0.0, 2, True),    # max_dis == width (largest legal range)
+    (80, 60, 16, 4, 3, -0.2, 2, True),   # reg_lambda < 0 (main.cc:34 accepts it): a negative scale weight, sums not monotone
+    (64, 48, 12, 4, 5, -0.3, 1, False),
 ])
 def test_full_patchmatch_bit_exact(cspm, orc_lib, w, h, d, scale, S, lam, iters, pp):
     if min(w, h) >= 8 and d >= 4:
@@ -270,6 +272,33 @@ def test_full_patchmatch_bit_exact(cspm, orc_lib, w, h, d, scale, S, lam, iters,
     evals_per_px = 1 + iters * (1 + mg.n_ref())
     assert st["plane_evals"] == 2 * w * h * evals_per_px + iters * 2 * ((w - 1) * h + w * (h - 1))
     assert st["kernel_launches"] > 0 and st["window_taps"] > 0
+
+
+@pytest.mark.parametrize("env", [
+    {"CSPM_SP_CTAS": "1"},                           # one CTA owns whole diagonals: up to 60 pixels, several passes of 32 tasks
+    {"CSPM_SP_CTAS": "3"},                           # partition neighbours with cnt > 1 on both sides
+    {"CSPM_WAVE_EXACT": "1"},                        # every task through the wavefront sweep's exact path
+    {"CSPM_WAVE_EXACT": "1", "CSPM_SP_CTAS": "2"},
+    {"CSPM_SPATIAL": "ring"},                        # round-1 sweep (serial add chains)
+    {"CSPM_SPATIAL": "ring", "CSPM_SP_CTAS": "3"},   # ... with 8-20 pixels per CTA and multi-pass diagonals
+    {"CSPM_SPATIAL": "diag"},                        # one launch per diagonal (fallback when a cooperative launch is refused)
+], ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
+def test_sweep_implementations_and_grid_caps(env):
+    """The sweep implementations and grid sizes that the default run on a 148-SM GPU never takes at these image
+    sizes: every CTA of the persistent grid owns at most one pixel of an 80x60 image, so the multi-pixel /
+    multi-pass / neighbour-wait paths are forced here with CSPM_SP_CTAS, and the alternative sweeps with
+    CSPM_SPATIAL / CSPM_WAVE_EXACT.  Each variant re-runs the oracle-checked stage and full-run tests."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("CSPM_NESTED_TEST"):
+        pytest.skip("nested run")
+    here = os.path.abspath(__file__)
+    sel = "test_stages_bit_exact or test_spatial_shortcuts or test_full_patchmatch_bit_exact or test_other_window_sizes"
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", sel],
+                         env={**os.environ, **env, "CSPM_NESTED_TEST": "1"}, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, f"{env}:\n{out.stdout[-3000:]}\n{out.stderr[-1500:]}"
 
 
 def test_error_behaviour(cspm, pair):
