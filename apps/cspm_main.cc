@@ -2,7 +2,10 @@
 // of include/cspm.hpp, with the same flag names (gflags syntax --name=value)
 // and the same constants (max_iter=3, wnd_size=35, scale_num=5).  Image I/O is
 // binary PPM (P6) in / PGM (P5) out: OpenCV's imread/imwrite are not available
-// here and image decoding is outside the hot path.
+// here and image decoding is outside the hot path.  --synth=WxHxD[:seed] generates the pair in memory with the
+// dependency-free generator of include/cspm_synth.h instead (the benchmark's inputs: --synth=1920x1080x256:0xC5B20003
+// is BASELINE.json's HD pair), in which case max_dis defaults to D and dis_scale to 1.  Extra flags beside the
+// reference's: --scale_num (main.cc:100 hard-codes 5), --schedule=raster|redblack, --seed, --device.
 //
 // build: g++ -O2 -std=c++17 -Iinclude apps/cspm_main.cc -o apps/cspm_main \
 //            -Lcrossscalepatchmatch_b200 -lcspm_b200 -Wl,-rpath,'$ORIGIN/../crossscalepatchmatch_b200'
@@ -15,6 +18,7 @@
 #include <string>
 
 #include "cspm.hpp"
+#include "cspm_synth.h"
 
 using namespace cspm;
 
@@ -49,7 +53,8 @@ int main(int argc, char** argv) {
                                           {"l_dis_file", "l_dis.pgm"}, {"r_dis_file", "r_dis.pgm"},
                                           {"max_dis", "0"}, {"dis_scale", "0"}, {"cc_name", "CCName"},
                                           {"use_cs", "false"}, {"use_pp", "false"}, {"reg_lambda", "0.0"},
-                                          {"seed", "24301"}, {"device", "0"}};
+                                          {"seed", "24301"}, {"device", "0"}, {"synth", ""}, {"scale_num", "5"},
+                                          {"schedule", "raster"}};
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     while (!a.empty() && a[0] == '-') a.erase(0, 1);
@@ -61,7 +66,21 @@ int main(int argc, char** argv) {
   }
   auto flag_true = [&](const char* k) { return F[k] == "true" || F[k] == "1"; };
   Mat l_img, r_img;
-  if (!read_ppm(F["l_img_file"], &l_img) || !read_ppm(F["r_img_file"], &r_img)) {
+  if (!F["synth"].empty()) {
+    int w = 0, h = 0, d = 0;
+    unsigned long long seed = CSPM_SYNTH_SEED_BASE;
+    char tail[64] = "";
+    if (std::sscanf(F["synth"].c_str(), "%dx%dx%d%63s", &w, &h, &d, tail) < 3 || w <= 0 || h <= 0 || d <= 0) {
+      std::cerr << "--synth expects WxHxD[:seed]" << std::endl;
+      return EXIT_FAILURE;
+    }
+    if (tail[0] == ':') seed = std::strtoull(tail + 1, nullptr, 0);
+    l_img = Mat(h, w, CV_8UC3);
+    r_img = Mat(h, w, CV_8UC3);
+    if (cspm_synth_pair(w, h, d, seed, l_img.data, r_img.data, nullptr) != 0) return EXIT_FAILURE;
+    if (F["max_dis"] == "0") F["max_dis"] = std::to_string(d);
+    if (F["dis_scale"] == "0") F["dis_scale"] = "1";
+  } else if (!read_ppm(F["l_img_file"], &l_img) || !read_ppm(F["r_img_file"], &r_img)) {
     std::cout << "Error: can not open image\n";  // main.cc:70-75
     return EXIT_FAILURE;
   }
@@ -72,7 +91,7 @@ int main(int argc, char** argv) {
     const int max_iter = 3, wnd_size = 35;
     IPlaneCost* plane_cost = nullptr;
     if (flag_true("use_cs")) {
-      const int scale_num = 5;  // main.cc:100
+      const int scale_num = std::atoi(F["scale_num"].c_str());  // main.cc:100 (5 there)
       plane_cost = new PreCSPC(l_img, r_img, std::atoi(F["max_dis"].c_str()), wnd_size, scale_num, cc_cost,
                                std::atof(F["reg_lambda"].c_str()), device);
     } else {
@@ -80,11 +99,13 @@ int main(int argc, char** argv) {
     }
     CSPatchMatch* patch_match = new CSPatchMatch(l_img, r_img, std::atoi(F["max_dis"].c_str()),
                                                  std::atoi(F["dis_scale"].c_str()),
-                                                 std::strtoull(F["seed"].c_str(), nullptr, 0), CSPM_SCHEDULE_RASTER, device);
+                                                 std::strtoull(F["seed"].c_str(), nullptr, 0),
+                                                 F["schedule"] == "redblack" ? CSPM_SCHEDULE_REDBLACK : CSPM_SCHEDULE_RASTER, device);
     patch_match->PatchMatch(max_iter, plane_cost, flag_true("use_pp"));
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "--------------------------------------------------------\n";
     std::cout << "Total Time: " << sec << std::endl;  // main.cc:122-125
+    std::cout << "Mpixel*disparities/s: " << (double)l_img.cols * l_img.rows * std::atoi(F["max_dis"].c_str()) / sec / 1e6 << std::endl;
     std::cout << "--------------------------------------------------------\n";
     write_pgm(F["l_dis_file"], patch_match->dis(kLeft));
     write_pgm(F["r_dis_file"], patch_match->dis(kRight));

@@ -45,10 +45,12 @@ sys.path.insert(0, ROOT)
 W_HD, H_HD, D_HD = 1920, 1080, 256
 ITERS = 3
 WND = 35
+PM_SEED = 0x5EED
 BYTES_PER_TAP = 19  # 3 B guide pixel + 2 x 8 B cost samples (pre_ss_pc.cc:93,109-110)
 # BASELINE.json configs: (w, h, max_dis, cross-scale S=3 lambda=0.3)
 CONFIGS = {"C1": (450, 375, 60, False), "C2": (450, 375, 60, True), "C3": (1242, 375, 128, True),
            "C4": (1920, 1080, 256, False), "C4cs": (1920, 1080, 256, True)}
+SCHEDULE_NAMES = {0: "raster", 1: "red-black (4 neighbours)", 2: "red-black (8 neighbours)"}
 CPU_CROP = (384, 216)  # bounded CPU sample (w, h), same max_dis: ~10-30 s of CPU work per pass
 
 
@@ -63,6 +65,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json config preset (default: C4, the headline)")
     ap.add_argument("--cpu-full", action="store_true", help="CPU arm on the whole image instead of the bounded crop (BASELINE.md table)")
+    ap.add_argument("--schedule", type=int, default=0, choices=[0, 1, 2],
+                    help="0 raster = the reference's order (headline), 1 / 2 red-black with 4 / 8 neighbours (throughput schedules)")
+    ap.add_argument("--no-worst-case", action="store_true", help="skip the extra step with early termination disabled")
+    ap.add_argument("--no-tap-count", action="store_true", help="skip the executed-tap count (instrumented build)")
     return ap.parse_args()
 
 
@@ -81,24 +87,40 @@ def workload(args):
 
 
 # ---------------------------------------------------------------- CPU arms
-def cpu_run(l, r, d, use_cs, nthreads):
-    """One pass of the reference's timed region on the CPU; returns (seconds, kind)."""
+def cpu_lib():
+    """The reference's own code if its build travelled with the repo (oracle/_ref: unmodified reference sources +
+    OpenCV shim; the -O3 -march=x86-64-v3 timing build when present), else the oracle port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
 
+    if orc.ref_fast_available():
+        return orc.ref_fast(), "reference", "-O3 -march=x86-64-v3 -fopenmp -ffp-contract=off (oracle/Makefile)"
     if orc.ref_available():
-        lib, kind = orc.ref(), "reference"
-        lib.set_time_mode(1)  # time(NULL) constant within the run, like a real clock within one second
-    else:
-        lib, kind = orc.oracle(), "port"
+        return orc.ref(), "reference", "-O2 -fopenmp -ffp-contract=off (oracle/Makefile)"
+    return orc.oracle(), "port", "-O2 -fopenmp -ffp-contract=off (oracle/Makefile)"
+
+
+def cpu_run(l, r, d, use_cs, nthreads, want_result=False):
+    """One pass of the reference's timed region (main.cc:92-123) on the CPU; returns (seconds, kind, build, result).
+    The reference's OpenMP row loops use `nthreads`; its time(NULL) seeds are interposed in the shim's mode 2
+    (every row gets the RNG stream id of the library's RNG contract, whatever the thread count), so the result
+    can be compared bit for bit with the GPU's."""
+    import orc
+
+    lib, kind, build = cpu_lib()
+    if kind == "reference":
+        lib.set_time_mode(2)
     t0 = time.perf_counter()
     pc = orc.PlaneCost(lib, l, r, d, WND, 3 if use_cs else 0, 0.3 if use_cs else 0.0)
-    pm = orc.PatchMatch(lib, l, r, d, 1)
+    pm = orc.PatchMatch(lib, l, r, d, 1, seed=PM_SEED)
     pm.patchmatch(ITERS, pc, False, nthreads)
     t = time.perf_counter() - t0
+    res = None
+    if want_result:
+        res = [pm.dis(0), pm.dis(1)] + [a for v in (0, 1) for a in pm.planes(v)]
     pm.close()
     pc.close()
-    return t, kind
+    return t, kind, build, res
 
 
 FULL_CPU = {"on": False}
@@ -113,6 +135,16 @@ def cpu_sample(w, h, d, seed):
     return np.ascontiguousarray(l[y0:y0 + ch, x0:x0 + cw]), np.ascontiguousarray(r[y0:y0 + ch, x0:x0 + cw]), cw, ch
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def sample_text(cw, ch, w, h, d):
+    if (cw, ch) == (w, h):
+        return f"the FULL {w}x{h} pair, max_dis={d}, full pipeline ({ITERS} iters)", "full"
+    return f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline ({ITERS} iters)", "crop"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -121,26 +153,67 @@ def run_reference(args):
     from crossscalepatchmatch_b200.synth import SEED_BASE
 
     l, r, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    kind = "port"
+    cores = host_cores()
+    kind, build = "port", ""
     for _ in range(min(args.warmup, 1)):  # one CPU warm-up pass is plenty (no JIT, no caches to prime)
         cpu_run(l, r, d, args.use_cs, cores)
     ts = []
     for _ in range(args.steps):
-        t, kind = cpu_run(l, r, d, args.use_cs, cores)
+        t, kind, build, _ = cpu_run(l, r, d, args.use_cs, cores)
         ts.append(t)
     total = sum(ts)
     value = cw * ch * d * args.steps / total / 1e6
-    sample = f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline ({ITERS} iters)"
+    sample, sample_kind = sample_text(cw, ch, w, h, d)
     line = {
         "impl": "reference", "metric": "Mpixel*disparities/s", "value": value, "unit": "Mpixel*disp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": name, "sample": sample, "sample_kind": sample_kind},
+        "cpu_baseline": {"value": value, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind, "sample": sample,
+                         "sample_kind": sample_kind, "build": build},
         "e2e": {"value": value, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # this arm is CPU only: the product library must not even be mapped into the process
+    line["product_so_loaded"] = any("libcspm_b200" in m for m in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None
     print(json.dumps(line), flush=True)
+
+
+def count_executed_taps(args, device):
+    """Window taps the PlaneRefinement launches actually execute: a second process loads the instrumented build
+    (libcspm_b200_count.so, -DCSPM_COUNT_TAPS=1: same kernels + a counter) and replays the step stage by stage."""
+    lib = os.path.join(ROOT, "crossscalepatchmatch_b200", "libcspm_b200_count.so")
+    if not os.path.exists(lib):
+        return None
+    w, h, d, _ = workload(args)
+    code = f"""
+import ctypes, json, sys
+sys.path.insert(0, {ROOT!r})
+import crossscalepatchmatch_b200 as c
+from crossscalepatchmatch_b200 import _lib
+from crossscalepatchmatch_b200.synth import SEED_BASE, make_pair
+l, r, _ = make_pair({w}, {h}, {d}, SEED_BASE + 3)
+cc = c.GetCCType("GRD")
+pc = c.PreCSPC(l, r, {d}, {WND}, 3, cc, 0.3, device={device}) if {bool(args.use_cs)} else c.PreSSPC(l, r, {d}, {WND}, cc, device={device})
+pm = c.CSPatchMatch(l, r, {d}, 1, seed={PM_SEED}, device={device}, schedule={args.schedule})
+n = ctypes.c_uint64(0)
+pm.stage(c.STAGE_INIT, 0, pc)
+tot = 0
+for it in range({ITERS}):
+    pm.stage(c.STAGE_SPATIAL, it, pc); pm.stage(c.STAGE_VIEW, it, pc)
+    _lib.check(_lib.dll.cspm_debug_taps_executed(ctypes.byref(n), 1))
+    pm.stage(c.STAGE_REFINE, it, pc)
+    _lib.check(_lib.dll.cspm_debug_taps_executed(ctypes.byref(n), 1))
+    tot += n.value
+print(json.dumps({{"refine_taps_per_launch": tot // {ITERS}}}))
+"""
+    try:
+        out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "CSPM_LIB_PATH": lib}, capture_output=True, text=True, timeout=600)
+        res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+        res["source"] = "libcspm_b200_count.so (-DCSPM_COUNT_TAPS=1) on the same inputs, mean of the step's 3 refinement launches"
+        return res
+    except Exception as e:  # the figure is an annotation: never fail the bench line over it
+        print(f"executed-tap count unavailable: {e}", file=sys.stderr)
+        return None
 
 
 # ------------------------------------------------------------- clock sampler
@@ -232,7 +305,7 @@ def run_b200(args):
     def step_device():
         """reference's timed region with inputs resident in HBM"""
         pc = make_pc(dl, dr, True)
-        pm = c.CSPatchMatch(None, None, d, 1, seed=0x5EED, device=local,
+        pm = c.CSPatchMatch(None, None, d, 1, seed=PM_SEED, device=local, schedule=args.schedule,
                             device_ptrs=((dl.data_ptr(), w, h, 3 * w), (dr.data_ptr(), w, h, 3 * w)))
         pm.PatchMatch(ITERS, pc, False)
         launches["n"] += pc.stats()["kernel_launches"] + pm.stats()["kernel_launches"]
@@ -241,7 +314,7 @@ def run_b200(args):
 
     def step_e2e():
         pc = make_pc(hl, hr, False)
-        pm = c.CSPatchMatch(hl.numpy(), hr.numpy(), d, 1, seed=0x5EED, device=local)
+        pm = c.CSPatchMatch(hl.numpy(), hr.numpy(), d, 1, seed=PM_SEED, device=local, schedule=args.schedule)
         pm.PatchMatch(ITERS, pc, False)
         return pm.dis(c.kLeft), pm.dis(c.kRight)
 
@@ -298,34 +371,86 @@ def run_b200(args):
         taps_launch = 2 * last["n_ref"] * last["taps_eval"]
         ms = float(np.mean(refine_ms))
         achieved = BYTES_PER_TAP * taps_launch / (ms * 1e-3) / 1e9
-        traffic = None
+        key = "cs" if args.use_cs else "ss"
+        traffic, onchip = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("cs" if args.use_cs else "ss")
+            traffic = json.load(open(tpath)).get(key)
+        opath = os.path.join(ROOT, "profiles", "r02_onchip.json")
+        if os.path.exists(opath):  # ncu --set full summary of the benched kernel version (profiles/summarize.py)
+            onchip = json.load(open(opath)).get("k_refine_" + key)
         stage_ms = dict(zip(["init", "spatial", "view", "refine", "plane2disp", "postproc"], last["stage_ms"]))
+        roofline = {"bound": "hbm", "kernel": "k_refine", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": BYTES_PER_TAP * taps_launch, "launch_ms": ms,
+                    "taps_nominal": int(taps_launch),
+                    "model": "no-reuse gather, 19 B per border-clipped window tap (SURVEY.md 8d): an upper bound on the "
+                             "bytes a cache-less machine would move, not DRAM traffic; windows of neighbouring pixels "
+                             "overlap 34/35 and are served by L1/L2, so frac > 1 is expected and the binding limits "
+                             "are the on-chip ones in `onchip`",
+                    "onchip": onchip}
+        if traffic:
+            roofline["dram_frac"] = traffic / (ms * 1e-3) / 1e9 / peak  # measured DRAM bytes / launch time / peak
+        # taps the launch really executed (exact early termination skips the rest): counted by the instrumented
+        # build of the same kernels on the same inputs, outside the timed region
+        if not args.no_tap_count:
+            ex = count_executed_taps(args, local)
+            if ex:
+                roofline["taps_executed"] = ex["refine_taps_per_launch"]
+                roofline["frac_executed"] = BYTES_PER_TAP * ex["refine_taps_per_launch"] / (ms * 1e-3) / 1e9 / peak
+                roofline["taps_executed_source"] = ex["source"]
         line = {
             "metric": "Mpixel*disparities/s", "value": value, "unit": "Mpixel*disp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "pairs_per_gpu_per_step": 1, "sharding": "one stereo pair per GPU, no data-path collective",
-                       "schedule": "raster (bit-exact reference order)", "l2": "flushed between timed steps (256 MiB write)"},
+                       "schedule": SCHEDULE_NAMES[args.schedule] + (" (bit-exact reference order)" if args.schedule == 0 else " (throughput schedule, not the reference's order)"),
+                       "l2": "flushed between timed steps (256 MiB write)"},
             "e2e": {"value": e2e, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 4 * w * h * 3, "d2h_bytes_per_step": 2 * w * h,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_refine", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_TAP * taps_launch, "launch_ms": ms,
-                         "model": "no-reuse gather, 19 B per border-clipped window tap (SURVEY.md 8d)"},
+            "roofline": roofline,
             "stage_ms": stage_ms,
             "window_taps_per_step": int(last["stats"]["window_taps"]),
+            "spatial_sweep": {k: int(last["stats"][k]) for k in ("spatial_tasks", "spatial_candidates", "spatial_adopted", "spatial_exact_tasks")},
         }
+        if world == 1 and not args.no_worst_case:
+            # data-independent figure: the same step with exact early termination switched off (every window summed in full)
+            os.environ["CSPM_NO_EARLY_TERM"] = "1"
+            step_device()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            a.record(stream)
+            step_device()
+            b.record(stream)
+            torch.cuda.synchronize()
+            del os.environ["CSPM_NO_EARLY_TERM"]
+            wms = a.elapsed_time(b)
+            line["worst_case"] = {"what": "exact early termination disabled (CSPM_NO_EARLY_TERM=1): every window summed in full, "
+                                          "throughput independent of the image content", "ms_per_step": wms,
+                                  "value": w * h * d / wms / 1e3, "unit": "Mpixel*disp/s",
+                                  "refine_frac_of_model": BYTES_PER_TAP * taps_launch / (last["stage_ms"][c.STAGE_REFINE] / ITERS * 1e-3) / 1e9 / peak}
         if world == 1 and not args.no_cpu_baseline:
             cl, cr, cw, ch = cpu_sample(w, h, d, SEED_BASE + 3)
-            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            t, kind = cpu_run(cl, cr, d, args.use_cs, cores)
+            cores = host_cores()
+            t, kind, build, ref_out = cpu_run(cl, cr, d, args.use_cs, cores, want_result=True)
+            sample, sample_kind = sample_text(cw, ch, w, h, d)
             line["cpu_baseline"] = {"value": cw * ch * d / t / 1e6, "unit": "Mpixel*disp/s", "cores": cores, "kind": kind,
-                                    "sample": f"{cw}x{ch} centre crop of the {w}x{h} pair, max_dis={d}, full pipeline, 1 pass ({t:.1f} s)"}
+                                    "sample": sample + f", 1 pass ({t:.1f} s)", "sample_kind": sample_kind, "build": build}
+            # parity on the very sample the CPU arm just computed: the GPU runs the same crop through the C ABI and
+            # both disparity maps and every plane / cost field must be bit-identical
+            if S == 0:
+                pcc = c.PreSSPC(cl, cr, d, WND, cc, device=local)
+            else:
+                pcc = c.PreCSPC(cl, cr, d, WND, S, cc, lam, device=local)
+            pmc = c.CSPatchMatch(cl, cr, d, 1, seed=PM_SEED, device=local, schedule=0)
+            pmc.PatchMatch(ITERS, pcc, False)
+            got = [pmc.dis(0), pmc.dis(1)] + [a for v in (0, 1) for a in pmc.planes(v)]
+            line["parity_checked"] = bool(all(np.array_equal(x, y) for x, y in zip(got, ref_out)))
+            line["parity_sample"] = sample + " (uint8 disparity maps, f64 normals / params / min_cost of both views, bit for bit" + (
+                "; GPU arm run with the raster schedule for this check)" if args.schedule else ")")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

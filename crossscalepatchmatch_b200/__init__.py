@@ -9,7 +9,7 @@ import importlib
 
 _API = ("CCMethod", "CenCC", "CSPC", "CSPatchMatch", "GrdPC", "GetCCType", "GrdCC", "IPlaneCost", "Plane", "PreCSPC",
         "PreSSPC", "kLeft", "kRight", "set_thread_stream", "PairBatch")
-_LIB = ("CspmError", "LIB_PATH", "SCHEDULE_RASTER", "SCHEDULE_REDBLACK", "STAGE_INIT", "STAGE_PLANE2DISP", "STAGE_POSTPROC",
+_LIB = ("CspmError", "LIB_PATH", "SCHEDULE_RASTER", "SCHEDULE_REDBLACK", "SCHEDULE_REDBLACK8", "STAGE_INIT", "STAGE_PLANE2DISP", "STAGE_POSTPROC",
         "STAGE_REFINE", "STAGE_SPATIAL", "STAGE_VIEW")
 __all__ = ["CspmError", "CCMethod", "GrdCC", "CenCC", "GetCCType", "IPlaneCost", "PreSSPC", "PreCSPC", "GrdPC", "CSPC", "Plane",
            "CSPatchMatch", "kLeft", "kRight", "LIB_PATH", "device_count"]

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CSPM_LIB_PATH") or os.path.join(_HERE, "libcspm_b200.so")
 
 OK, EINVAL, ENODEV, ENOMEM, EUNSUPPORTED, ECUDA = 0, -1, -2, -3, -4, -5
-SCHEDULE_RASTER, SCHEDULE_REDBLACK = 0, 1
+SCHEDULE_RASTER, SCHEDULE_REDBLACK, SCHEDULE_REDBLACK8 = 0, 1, 2
 STAGE_INIT, STAGE_SPATIAL, STAGE_VIEW, STAGE_REFINE, STAGE_PLANE2DISP, STAGE_POSTPROC = range(6)
 
 

@@ -76,6 +76,8 @@ struct PcDev {
   int monotone;                // 1: every scale weight is >= 0, so running sums never decrease (exact early termination
                                // and the certified comparisons of the wavefront sweep rely on it); 0 (reg_lambda < 0
                                // can give negative weights): every cost is summed in full
+  int early_term;              // monotone, and not switched off for measurements (CSPM_NO_EARLY_TERM=1 when the plane
+                               // cost is created): the bulk kernels stop a window sum once it has reached the bound
   ScaleDev sc[kMaxScales];
   double scale_wgt[kMaxScales];
   const double* lut_w;         // [kLutW]
@@ -588,7 +590,7 @@ __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int
                                              const double* lut_w, const double* lut_c, double bound) {
   // (bound is a by-value copy: callers keep comparing against their own)
   const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
-  if (cross && !pc.monotone) bound = __longlong_as_double(0x7ff0000000000000ll);  // negative scale weights: no early termination
+  if (!pc.early_term) bound = __longlong_as_double(0x7ff0000000000000ll);  // sums not monotone (negative scale weight), or switched off
   if (!cross) return window_cost<CC, LWS, CSM, COOP>(pc, 0, v, rx, ry, p.a, p.b, p.c, lut_w, lut_c, bound, 0.0, 1.0);
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);

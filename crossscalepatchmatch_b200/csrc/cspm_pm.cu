@@ -117,6 +117,53 @@ __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_refine(PcDev 
   store_plane(pm.st[v], n, i, cur, cur_cost);
 }
 
+// --------------------------------------------------------------- red-black
+// CSPM_SCHEDULE_REDBLACK / _REDBLACK8: SpatialPropagation as two checkerboard half-sweeps per iteration (the
+// throughput schedule BASELINE.json's north_star names; NOT the reference's raster order — bit-identical to the
+// oracle's schedule 1 / 2, oracle.cc SpatialPropagationRedBlack).  One half-sweep = one launch: thread per pixel
+// of the active colour, candidates = the planes of (x-1,y), (x+1,y), (x,y-1), (x,y+1) [+ the same at distance 5],
+// in that order, each tested against the running minimum with the strict `<`.  All offsets are odd, so the
+// neighbours have the other colour and nobody writes them during the launch: no ordering between threads.
+// Same bulk evaluator as refinement (exact early termination against the running minimum, cooperative tail).
+__device__ __forceinline__ bool plane_bits_eq(const PlaneD& p, const PlaneD& q) {
+  auto eq = [](double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); };
+  return eq(p.a, q.a) && eq(p.b, q.b) && eq(p.c, q.c) && eq(p.nx, q.nx) && eq(p.ny, q.ny) && eq(p.nz, q.nz);
+}
+template <int CC, bool CS>
+__global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_redblack(PcDev pc, PmDev pm, int colour, int noff) {
+  extern __shared__ __align__(16) double s_dyn[];
+  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
+  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  tma_stage_luts_begin(pc, s_dyn, s_mbar);
+  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((y + colour) & 1);
+  const int v = blockIdx.z;
+  if (x >= pm.w || y >= pm.h) return;
+  const size_t n = (size_t)pm.w * pm.h, i = (size_t)y * pm.w + x;
+  PlaneD cur = load_plane(pm.st[v], n, i);
+  double cur_cost = pm.st[v][6 * n + i];
+  bool adopted = false;
+  tma_stage_luts_wait(s_mbar);
+  for (int k = 0; k < noff; ++k) {
+    const int o = k < 4 ? 1 : 5;
+    const int nx = x + ((k & 2) ? 0 : ((k & 1) ? o : -o)), ny = y + ((k & 2) ? ((k & 1) ? o : -o) : 0);
+    if (nx < 0 || nx >= pm.w || ny < 0 || ny >= pm.h) continue;
+    const PlaneD cand = load_plane(pm.st[v], n, (size_t)ny * pm.w + nx);
+    // exact shortcut: a candidate that is bitwise the plane the pixel currently holds costs exactly cur_cost
+    // (if that plane was adopted in this launch, or — while every stored cost is known to be GetPlaneCost of its
+    // plane — if it is the pixel's own) and cannot pass the strict `<`
+    if ((adopted || pm.cost_consistent) && plane_bits_eq(cand, cur)) continue;
+    const double cost = plane_cost<CC, kLutRepShift, CS ? 1 : 0>(pc, v, x, y, cand, s_lut_w, s_lut_c, cur_cost);
+    if (cost < cur_cost) {
+      cur = cand;
+      cur_cost = cost;
+      adopted = true;
+    }
+  }
+  if (adopted) store_plane(pm.st[v], n, i, cur, cur_cost);
+}
+
 // ---------------------------------------------------------------- spatial
 // One anti-diagonal of the serial raster scan.  Pixel (u,t) in scan
 // coordinates (u+t == diag) depends only on (u-1,t) and (u,t-1), both final
@@ -484,7 +531,30 @@ static int spatial_cta_cap() {
   return e ? std::max(1, atoi(e)) : 0;
 }
 
+static void run_redblack(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  note_cost_writer(pm, pc, false);
+  PmDev d = pm_dev(pm);
+  d.cost_consistent = pm->cost_owner == pc->uid;
+  const int noff = pm->schedule == CSPM_SCHEDULE_REDBLACK8 ? 8 : 4;
+  for (int half = 0; half < 2; ++half) {
+    const int colour = (iter + half) & 1;
+    CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = bulk_by<CS>(); dim3 b(32, by), g(((pm->w + 1) / 2 + 31) / 32, (pm->h + by - 1) / by, 2);
+                        bulk_smem(k_redblack<CC, CS>); k_redblack<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, d, colour, noff));
+    pm->stats.kernel_launches++;
+  }
+  // every pixel is active in exactly one half-sweep; one evaluation per in-image neighbour (duplicates included)
+  uint64_t ev = 0;
+  for (int k = 0; k < noff; ++k) {
+    const int o = k < 4 ? 1 : 5;
+    const int ox = (k & 2) ? 0 : o, oy = (k & 2) ? o : 0;
+    ev += 2ull * (uint64_t)std::max(0, pm->w - ox) * (uint64_t)std::max(0, pm->h - oy);
+  }
+  pm->stats.plane_evals += ev;
+  pm->stats.window_taps += (uint64_t)((double)pc->taps_per_image_eval * ((double)ev / ((double)pm->w * pm->h)));
+}
+
 static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
+  if (pm->schedule != CSPM_SCHEDULE_RASTER) return run_redblack(pm, pc, iter);
   const int rev = (iter % 2 == 0) ? 0 : 1;
   const int wnd = 2 * pc->dev.half_wnd + 1;
   note_cost_writer(pm, pc, false);
@@ -648,7 +718,8 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
     // ViewPropagation wraps x +- round(d) ONCE (HandleBorder, commfunc.h:129-145); with max_dis > width the
     // reference indexes past its row arrays (undefined behaviour), so that domain is rejected here.
     CSPM_REQUIRE(max_dis <= w, "max_dis must not exceed the image width (single wrap-around in ViewPropagation)");
-    if (schedule != CSPM_SCHEDULE_RASTER) throw Error(CSPM_EUNSUPPORTED, "only CSPM_SCHEDULE_RASTER is implemented");
+    CSPM_REQUIRE(schedule == CSPM_SCHEDULE_RASTER || schedule == CSPM_SCHEDULE_REDBLACK || schedule == CSPM_SCHEDULE_REDBLACK8,
+                 "unknown schedule");
     use_device(device);
     cspm_pm* pm = new cspm_pm();
     try {
@@ -866,8 +937,12 @@ int cspm_debug_counters(unsigned long long* out8, int reset) {
   return guard([&] {
     CSPM_REQUIRE(out8, "null argument");
     CSPM_CUDA(cudaDeviceSynchronize());
+#if CSPM_WAVE_PROFILE
+    CSPM_CUDA(cudaMemcpyFromSymbol(out8, g_sp_prof, sizeof(unsigned long long) * 8));
+#else
     CSPM_CUDA(cudaMemcpyFromSymbol(out8, g_sp_prof, sizeof(unsigned long long) * 4));
     CSPM_CUDA(cudaMemcpyFromSymbol(out8 + 4, g_eng_prof, sizeof(unsigned long long) * 4));
+#endif
     if (reset) {
       unsigned long long z[8] = {};
       CSPM_CUDA(cudaMemcpyToSymbol(g_sp_prof, z, sizeof z));

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
 #endif
       // both candidates must beat the pixel's cost at the start of the step (cs_patchmatch.cc:201,209)
       // (negative scale weights, reg_lambda < 0: sums are not monotone, no early termination)
-      const double ch_bound = pc.monotone ? __shfl_sync(0xffffffffu, ch_min, lane & ~1) : CUDART_INF;
+      const double ch_bound = pc.early_term ? __shfl_sync(0xffffffffu, ch_min, lane & ~1) : CUDART_INF;
       SP_PROF(0);
       const double ch_cost = WND == 35
           ? engine_eval_pairs_ring<CC, kSpThreads>(pc, rs, 2 * nt, ch_on, ch_v, ch_x, ch_y, ch_plane, ch_bound)

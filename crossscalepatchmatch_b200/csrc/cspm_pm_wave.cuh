@@ -36,6 +36,23 @@
 #define CSPM_WAVE_UNROLL 2
 #endif
 
+// -DCSPM_WAVE_PROFILE=1: cycle accounting of one CTA (grid / 2), read back with cspm_debug_counters:
+// {neighbour wait, barrier, evaluation (warp 0), wait for the slowest warp, decision, barrier, publish, diagonals}
+#ifndef CSPM_WAVE_PROFILE
+#define CSPM_WAVE_PROFILE 0
+#endif
+#if CSPM_WAVE_PROFILE
+#define WV_PROF(slot)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) {              \
+      const long long now__ = clock64();                                \
+      g_sp_prof[slot] += (unsigned long long)(now__ - prof_t);          \
+      prof_t = now__;                                                   \
+    }                                                                   \
+  } while (0)
+#else
+#define WV_PROF(slot) do { } while (0)
+#endif
 constexpr int kWvThreads = CSPM_WAVE_THREADS;
 constexpr int kWvWarps = kWvThreads / 32;
 constexpr int kWvTasks = 32;  // tasks per pass (a CTA owns <= 8 pixels x 2 views per diagonal at HD)
@@ -184,6 +201,9 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
   if (threadIdx.x == 0) ctl->n_amb = 0;
   unsigned int st_tasks = 0, st_cands = 0, st_fast = 0, st_exact = 0;
   tma_stage_luts_wait(s_mbar);
+#if CSPM_WAVE_PROFILE
+  long long prof_t = clock64();
+#endif
 
   for (int diag = 1; diag <= pm.w + pm.h - 2; ++diag) {
     const int u_lo = max(0, diag - (pm.h - 1)), u_hi = min(diag, pm.w - 1);
@@ -212,7 +232,9 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         } while ((int)seen < diag - 1);
       }
     }
+    WV_PROF(0);
     __syncthreads();
+    WV_PROF(1);
     for (int base = 0; base < ntasks_mine; base += kWvTasks) {
       const int nt = min(kWvTasks, ntasks_mine - base);
       // ---------------------------------------------------------------- evaluate: tree sums of all candidates
@@ -291,7 +313,9 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         const double r0 = wave_warp_sum(acc0), r1 = wave_warp_sum(acc1);
         if (lane == 0) { ctl->partial[warp][cur_task - first_task][0] = r0; ctl->partial[warp][cur_task - first_task][1] = r1; }
       }
+      WV_PROF(2);
       __syncthreads();
+      WV_PROF(3);
       // ---------------------------------------------------------------- decide: certified comparisons
       if (warp == 0 && lane < nt) {
         const WvTask& T = ctl->task[lane];
@@ -333,7 +357,9 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
           st_fast += 1;
         }
       }
+      WV_PROF(4);
       __syncthreads();
+      WV_PROF(5);
       // ---------------------------------------------------------------- exact path for the undecided tasks (rare)
       const int n_amb = ctl->n_amb;
       if (n_amb > 0) {
@@ -362,6 +388,10 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
     // (release is cumulative); one store per CTA and diagonal
     if (threadIdx.x == 0)
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + 32 * blockIdx.x), "r"((unsigned int)diag) : "memory");
+    WV_PROF(6);
+#if CSPM_WAVE_PROFILE
+    if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_sp_prof[7] += 1;
+#endif
   }
   if (warp == 0) {
 #pragma unroll

@@ -36,6 +36,11 @@ struct Exception : std::runtime_error {  // stands in for cv::Exception (CV_Asse
 inline void check(int rc) {
   if (rc < 0) throw Exception(rc, cspm_last_error());
 }
+// a creator returned NULL: throw with the code the library recorded (EINVAL / ENODEV / ENOMEM / EUNSUPPORTED / ECUDA)
+[[noreturn]] inline void throw_last() {
+  const int code = cspm_last_error_code();
+  throw Exception(code < 0 ? code : CSPM_EINVAL, cspm_last_error());
+}
 
 // Minimal cv::Mat stand-in.
 class Mat {
@@ -60,6 +65,11 @@ class Mat {
   int type_ = CV_8UC1;
   std::vector<uint8_t> own_;
 };
+
+// CV_Assert(l_img.type() == CV_8UC3 && r_img.type() == CV_8UC3) (pre_ss_pc.cc:24, cs_patchmatch.cc:8) — plus the
+// geometry the reference takes for granted (it indexes the right image with the left image's sizes): one
+// rows / cols / step for both images, because the C ABI receives a single (w, h, stride).
+inline void require_pair_8uc3(const class Mat& l, const class Mat& r);
 
 // plane.h:12-48
 class Plane {
@@ -90,7 +100,7 @@ class CCMethod {
 
  protected:
   explicit CCMethod(const char* name) : h_(cspm_cc_create(name)) {
-    if (!h_) throw Exception(CSPM_EINVAL, cspm_last_error());
+    if (!h_) throw_last();
   }
 
  private:
@@ -147,19 +157,22 @@ class IPlaneCost {
 
  protected:
   IPlaneCost() {}
-  static void require_8uc3(const Mat& l, const Mat& r) {  // CV_Assert, pre_ss_pc.cc:24
-    if (l.type() != CV_8UC3 || r.type() != CV_8UC3 || l.rows != r.rows || l.cols != r.cols || l.step != r.step)
-      throw Exception(CSPM_EINVAL, "CV_Assert(l_img.type() == CV_8UC3 && r_img.type() == CV_8UC3)");
-  }
+  static void require_8uc3(const Mat& l, const Mat& r) { require_pair_8uc3(l, r); }
   cspm_pc_t* h_ = nullptr;
 };
+inline void require_pair_8uc3(const Mat& l, const Mat& r) {
+  if (l.type() != CV_8UC3 || r.type() != CV_8UC3)
+    throw Exception(CSPM_EINVAL, "CV_Assert(l_img.type() == CV_8UC3 && r_img.type() == CV_8UC3)");
+  if (!l.data || !r.data || l.rows != r.rows || l.cols != r.cols || l.step != r.step)
+    throw Exception(CSPM_EINVAL, "left and right image must have the same rows, cols and step");
+}
 class PreSSPC : public IPlaneCost {  // plane_cost/pre_ss_pc.h:18-52
  public:
   PreSSPC(const Mat& l_img, const Mat& r_img, const int& max_disp, const int& wnd_size, CCMethod* cc_method, int device = 0) {
     require_8uc3(l_img, r_img);
     h_ = cspm_pc_create_ss(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size,
                            cc_method ? cc_method->handle() : nullptr, device);
-    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+    if (!h_) throw_last();
   }
 };
 class PreCSPC : public IPlaneCost {  // plane_cost/pre_cs_pc.h:19-62
@@ -169,7 +182,7 @@ class PreCSPC : public IPlaneCost {  // plane_cost/pre_cs_pc.h:19-62
     require_8uc3(l_img, r_img);
     h_ = cspm_pc_create_cs(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size,
                            scale_num, cc_method ? cc_method->handle() : nullptr, reg_lambda, device);
-    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+    if (!h_) throw_last();
   }
 };
 
@@ -178,7 +191,7 @@ class GrdPC : public IPlaneCost {  // plane_cost/grd_pc.h:19-71
   GrdPC(const Mat& l_img, const Mat& r_img, const int& max_disp, const int& wnd_size, int device = 0) {
     require_8uc3(l_img, r_img);
     h_ = cspm_pc_create_grdpc(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size, device);
-    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+    if (!h_) throw_last();
   }
 };
 class CSPC : public IPlaneCost {  // plane_cost/cspc.h:17-62
@@ -188,7 +201,7 @@ class CSPC : public IPlaneCost {  // plane_cost/cspc.h:17-62
     require_8uc3(l_img, r_img);
     h_ = cspm_pc_create_cspc(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_disp, wnd_size,
                              scale_num, reg_lambda, device);
-    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+    if (!h_) throw_last();
   }
 };
 
@@ -197,17 +210,23 @@ class CSPatchMatch {
  public:
   CSPatchMatch(const Mat& l_img, const Mat& r_img, const int& max_dis, const int& dis_scale, uint64_t seed = 0x5EED,
                int schedule = CSPM_SCHEDULE_RASTER, int device = 0) {
-    if (l_img.type() != CV_8UC3 || r_img.type() != CV_8UC3)  // CV_Assert, cs_patchmatch.cc:8
-      throw Exception(CSPM_EINVAL, "CV_Assert(l_img.type() == CV_8UC3 && r_img.type() == CV_8UC3)");
+    require_pair_8uc3(l_img, r_img);  // CV_Assert, cs_patchmatch.cc:8
     h_ = cspm_pm_create(l_img.data, r_img.data, l_img.cols, l_img.rows, (int)l_img.step, max_dis, dis_scale, seed,
                         schedule, device);
-    if (!h_) throw Exception(CSPM_ENODEV, cspm_last_error());
+    if (!h_) throw_last();
     for (int v = 0; v < 2; ++v) dis_[v] = Mat::zeros(l_img.rows, l_img.cols, CV_8UC1);
   }
   ~CSPatchMatch() { cspm_pm_destroy(h_); }
   CSPatchMatch(const CSPatchMatch&) = delete;
   CSPatchMatch& operator=(const CSPatchMatch&) = delete;
+  // The reference accepts any `const IPlaneCost*` and calls its virtual GetPlaneCost 43 x W x H x 2 times
+  // (cs_patchmatch.h:65-66).  Here the plane cost is fused into the kernels, so only plane costs built by this
+  // library (PreSSPC, PreCSPC, GrdPC, CSPC: handle() != NULL) can drive PatchMatch; a user-defined IPlaneCost
+  // subclass is rejected with CSPM_EUNSUPPORTED instead of being evaluated on the host (no CPU fallback).
   void PatchMatch(const int& iter_num, const IPlaneCost* plane_cost, const bool& use_pp) {
+    if (plane_cost && !plane_cost->handle())
+      throw Exception(CSPM_EUNSUPPORTED, "PatchMatch needs a plane cost built by libcspm_b200 (PreSSPC / PreCSPC / GrdPC / CSPC); "
+                                         "user-defined IPlaneCost subclasses cannot be fused into the kernels");
     check(cspm_pm_patchmatch(h_, iter_num, plane_cost ? plane_cost->handle() : nullptr, use_pp ? 1 : 0));
     for (int v = 0; v < 2; ++v) check(cspm_pm_get_dis(h_, v, dis_[v].data, (int)dis_[v].step));
   }

@@ -49,13 +49,16 @@ extern "C" {
 #define CSPM_VIEW_LEFT 0  /* RefView::kLeft,  commfunc.h:29 */
 #define CSPM_VIEW_RIGHT 1 /* RefView::kRight */
 
-/* Propagation schedules.  RASTER reproduces the reference's serial
- * Gauss-Seidel scans exactly (spatial: anti-diagonal wavefront; view: scatter
- * with first-in-scan-order tie-break) — results are bit-identical to the
- * reference code.  REDBLACK is the throughput schedule (checkerboard sweeps);
- * it is bit-identical to oracle schedule "redblack", not to the raster scan. */
+/* Propagation schedules of SpatialPropagation (the other stages are the same in all of them).
+ * RASTER reproduces the reference's serial Gauss-Seidel scan exactly (anti-diagonal wavefront): results are
+ * bit-identical to the reference code.  REDBLACK / REDBLACK8 are the throughput schedules (not in the reference;
+ * BASELINE.json's north_star names them): iteration i makes two checkerboard half-sweeps, colour (i + half) & 1
+ * first; a pixel of the active colour tests, in this order, the planes of (x-1,y), (x+1,y), (x,y-1), (x,y+1) —
+ * REDBLACK8 then also (x-5,y), (x+5,y), (x,y-5), (x,y+5) — against its running minimum with the strict `<`.
+ * Bit-identical to the oracle's schedule 1 / 2 (oracle/oracle.cc SpatialPropagationRedBlack), not to the raster scan. */
 #define CSPM_SCHEDULE_RASTER 0
 #define CSPM_SCHEDULE_REDBLACK 1
+#define CSPM_SCHEDULE_REDBLACK8 2
 
 /* PatchMatch stages for cspm_pm_stage (parity tests drive them one by one). */
 #define CSPM_STAGE_INIT 0       /* InitRandomPlane     cs_patchmatch.cc:115-148 */

@@ -648,6 +648,40 @@ struct CSPatchMatch {  // cs_patchmatch.{h,cc}
       }
     }
   }
+  // Throughput schedule named in BASELINE.json's north_star (NOT in the reference; restated here so that the
+  // kernel has a schedule-matched oracle, include/cspm_c.h CSPM_SCHEDULE_REDBLACK / _REDBLACK8): instead of the
+  // raster Gauss-Seidel scan, iteration i makes two checkerboard half-sweeps, colour (i + half) & 1 first.  A pixel
+  // (x, y) of the active colour tests, in this order, the planes of (x-1,y), (x+1,y), (x,y-1), (x,y+1) — and with
+  // far8 also (x-5,y), (x+5,y), (x,y-5), (x,y+5) — against its running minimum with the reference's strict `<`.
+  // All offsets are odd, so every neighbour has the other colour and is not modified during the half-sweep:
+  // the result does not depend on the order in which the active pixels are processed.
+  void SpatialPropagationRedBlack(int cur_iter, const IPlaneCost* pc, bool far8) {
+    static const int kOff[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-5, 0}, {5, 0}, {0, -5}, {0, 5}};
+    const int noff = far8 ? 8 : 4;
+    for (int half = 0; half < 2; ++half) {
+      const int colour = (cur_iter + half) & 1;
+      for (int v = kLeft; v <= kRight; ++v) {
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < hei_; ++y)
+          for (int x = (y + colour) & 1; x < wid_; x += 2)
+            for (int k = 0; k < noff; ++k) {
+              const int nx = x + kOff[k][0], ny = y + kOff[k][1];
+              if (nx < 0 || nx >= wid_ || ny < 0 || ny >= hei_) continue;
+              const Plane cand = P(v, ny, nx);
+              const double cost = pc->GetPlaneCost(x, y, cand, (RefView)v);
+              if (cost < C(v, y, x)) {
+                C(v, y, x) = cost;
+                P(v, y, x) = cand;
+              }
+            }
+      }
+    }
+  }
+  int schedule_ = 0;  // 0 raster (the reference), 1 red-black 4-neighbour, 2 red-black 8-neighbour
+  void Spatial(int cur_iter, const IPlaneCost* pc) {
+    if (schedule_ == 0) SpatialPropagation(cur_iter, pc);
+    else SpatialPropagationRedBlack(cur_iter, pc, schedule_ == 2);
+  }
   // cs_patchmatch.cc:229-277
   void ViewPropagation(int cur_iter, const IPlaneCost* pc) {
     Plane cor_plane;
@@ -852,7 +886,7 @@ struct CSPatchMatch {  // cs_patchmatch.{h,cc}
   void PatchMatch(int iter_num, const IPlaneCost* pc, bool use_pp) {
     InitRandomPlane(pc);
     for (int i = 0; i < iter_num; ++i) {
-      SpatialPropagation(i, pc);
+      Spatial(i, pc);
       ViewPropagation(i, pc);
       PlaneRefinement(i, max_dis_ / 2.0, kMaxNorm_, kZStopThres_, pc);
     }
@@ -981,6 +1015,8 @@ void* orc_pm_create(const uint8_t* l, const uint8_t* r, int w, int h, int stride
   return new CSPatchMatch(load_img(l, w, h, stride), load_img(r, w, h, stride), max_dis, dis_scale, seed);
 }
 void orc_pm_destroy(void* pm) { delete (CSPatchMatch*)pm; }
+// 0 raster (reference order), 1 / 2 red-black with 4 / 8 neighbours (see SpatialPropagationRedBlack)
+void orc_pm_set_schedule(void* pm, int schedule) { ((CSPatchMatch*)pm)->schedule_ = schedule; }
 int orc_pm_n_ref(const void* pm) { return ((const CSPatchMatch*)pm)->n_ref(); }
 void orc_pm_patchmatch(void* pm, int iter_num, const void* pc, int use_pp, int nthreads) {
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -993,7 +1029,7 @@ void orc_pm_stage(void* pm_, int stage, int iter, const void* pc_, int nthreads)
   if (nthreads > 0) omp_set_num_threads(nthreads);
   switch (stage) {
     case 0: pm->InitRandomPlane(pc); break;
-    case 1: pm->SpatialPropagation(iter, pc); break;
+    case 1: pm->Spatial(iter, pc); break;
     case 2: pm->ViewPropagation(iter, pc); break;
     case 3: pm->PlaneRefinement(iter, pm->max_dis_ / 2.0, pm->kMaxNorm_, pm->kZStopThres_, pc); break;
     case 4: pm->PlaneToDisp(); break;

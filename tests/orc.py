@@ -58,6 +58,7 @@ class Lib:
             f("rng_normal3", None, [C.c_uint64, C.c_uint64, C.c_uint32, _dp])
             f("plane_param", None, [_dp, _dp, _dp])
             f("pm_n_ref", C.c_int, [C.c_void_p])
+            f("pm_set_schedule", None, [C.c_void_p, C.c_int])
         else:
             f("set_seed", None, [C.c_uint64])
             f("set_time_mode", None, [C.c_int])
@@ -131,13 +132,15 @@ class PlaneCost:
 class PatchMatch:
     INIT, SPATIAL, VIEW, REFINE, PLANE2DISP, POSTPROC = range(6)
 
-    def __init__(self, lib: Lib, l, r, max_dis, dis_scale, seed=0x5EED):
+    def __init__(self, lib: Lib, l, r, max_dis, dis_scale, seed=0x5EED, schedule=0):
         self.lib = lib
         self.l = np.ascontiguousarray(l, np.uint8)
         self.r = np.ascontiguousarray(r, np.uint8)
         self.h, self.w, _ = self.l.shape
         self.h_ = lib.pm_create(_ptr(self.l, _u8p), _ptr(self.r, _u8p), self.w, self.h, self.l.strides[0], max_dis,
                                 dis_scale, seed)
+        if schedule:
+            lib.pm_set_schedule(self.h_, schedule)  # oracle only: the reference has no such schedule
 
     def close(self):
         if self.h_:

@@ -301,6 +301,36 @@ def test_sweep_implementations_and_grid_caps(env):
     assert out.returncode == 0, f"{env}:\n{out.stdout[-3000:]}\n{out.stderr[-1500:]}"
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("S,lam", [(0, 0.0), (3, 0.3)])
+def test_redblack_schedules_match_oracle(cspm, orc_lib, pair, schedule, S, lam):
+    """CSPM_SCHEDULE_REDBLACK (4 neighbours) / _REDBLACK8 (+ the four at distance 5): checkerboard half-sweeps
+    instead of the raster scan (include/cspm_c.h).  Not the reference's order — checked bit for bit against the
+    oracle's restatement of the same schedule, stage by stage and as a full run; and it must differ from raster."""
+    l, r = pair
+    cc = cspm.GetCCType("GRD")
+    po = orc.PlaneCost(orc_lib, l, r, D, 35, S, lam)
+    pg = cspm.PreSSPC(l, r, D, 35, cc) if S == 0 else cspm.PreCSPC(l, r, D, 35, S, cc, lam)
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=11, schedule=schedule)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=11, schedule=schedule)
+    mo.stage(orc.PatchMatch.INIT, 0, po)
+    mg.stage(cspm.STAGE_INIT, 0, pg)
+    for it in range(2):
+        mo.stage(orc.PatchMatch.SPATIAL, it, po)
+        mg.stage(cspm.STAGE_SPATIAL, it, pg)
+        _same_state(mo, mg, f"red-black sweep {it}")
+    mo = orc.PatchMatch(orc_lib, l, r, D, 4, seed=11, schedule=schedule)
+    mg = cspm.CSPatchMatch(l, r, D, 4, seed=11, schedule=schedule)
+    mo.patchmatch(2, po, True)
+    mg.PatchMatch(2, pg, True)
+    _same_state(mo, mg, "red-black full run")
+    for v in (0, 1):
+        assert np.array_equal(mo.dis(v), mg.dis(v))
+    raster = cspm.CSPatchMatch(l, r, D, 4, seed=11)
+    raster.PatchMatch(2, pg, True)
+    assert not np.array_equal(raster.planes(0)[1], mg.planes(0)[1])
+
+
 def test_error_behaviour(cspm, pair):
     l, r = pair
     assert cspm.GetCCType("BSM") is None            # main.cc:47-54
@@ -315,6 +345,9 @@ def test_error_behaviour(cspm, pair):
         pg.GetPlaneCostBatch([W], [0], [[0, 0, 1.0]], [[0, 0, 1.0]], [0])  # pixel outside the image
     with pytest.raises(cspm.CspmError):
         cspm.CSPatchMatch(l[:, :16].copy(), r[:, :16].copy(), 17, 1)  # max_dis > width: UB in the reference, rejected
+    with pytest.raises(cspm.CspmError) as ei:
+        cspm.CSPatchMatch(l, r, D, 4, schedule=7)     # unknown schedule
+    assert ei.value.code == -1                       # CSPM_EINVAL travels through the NULL-returning creator
     small = cspm.CSPatchMatch(l[:32, :32].copy(), r[:32, :32].copy(), D, 4)
     with pytest.raises(cspm.CspmError):
         small.PatchMatch(1, pg)                      # geometry mismatch
