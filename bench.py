@@ -105,9 +105,8 @@ def cpu_run(l, r, d, use_cs, nthreads, want_result=False):
     The reference's OpenMP row loops use `nthreads`; its time(NULL) seeds are interposed in the shim's mode 2
     (every row gets the RNG stream id of the library's RNG contract, whatever the thread count), so the result
     can be compared bit for bit with the GPU's."""
-    import orc
-
     lib, kind, build = cpu_lib()
+    import orc
     if kind == "reference":
         lib.set_time_mode(2)
     t0 = time.perf_counter()

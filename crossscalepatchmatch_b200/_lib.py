@@ -72,6 +72,7 @@ SIGNATURES = {
     "cspm_pc_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cspm_pm_stage_ms": (C.c_int, [C.c_void_p, _fp]),
     "cspm_debug_counters": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
+    "cspm_debug_wave_samples": (C.c_int, [_dp, C.POINTER(C.c_uint32)]),
     "cspm_debug_lane_hist": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
 }
 

@@ -70,7 +70,7 @@ class CCMethod:
         self.name = name
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and dll is not None:  # (module globals are gone at interpreter shutdown)
             dll.cspm_cc_destroy(self._h)
             self._h = None
 
@@ -117,7 +117,7 @@ class IPlaneCost:
     _h = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and dll is not None:  # (module globals are gone at interpreter shutdown)
             dll.cspm_pc_destroy(self._h)
             self._h = None
 
@@ -246,7 +246,7 @@ class CSPatchMatch:
             _lib.raise_last()
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and dll is not None:  # (module globals are gone at interpreter shutdown)
             dll.cspm_pm_destroy(self._h)
             self._h = None
 

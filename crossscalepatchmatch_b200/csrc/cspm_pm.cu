@@ -518,12 +518,12 @@ static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
 // cspm_pm_wave.cuh), "ring" (round 1: streaming evaluator with one serial add chain per candidate,
 // cspm_pm_engine.cuh) or "diag" (one launch per anti-diagonal).  All three are bit-identical; the environment
 // variable CSPM_SPATIAL exists for A/B measurements and for the tests that cross-check them.
-enum SpatialMode { SP_WAVE = 0, SP_RING = 1, SP_DIAG = 2 };
+enum SpatialMode { SP_AUTO = -1, SP_WAVE = 0, SP_RING = 1, SP_DIAG = 2 };
 static SpatialMode spatial_mode() {
   const char* e = getenv("CSPM_SPATIAL");
-  if (!e) return SP_WAVE;
+  if (!e) return SP_AUTO;
   const std::string m(e);
-  return m == "diag" ? SP_DIAG : m == "ring" ? SP_RING : SP_WAVE;
+  return m == "diag" ? SP_DIAG : m == "ring" ? SP_RING : m == "wave" ? SP_WAVE : SP_AUTO;
 }
 // CSPM_SP_CTAS=n caps the persistent grid (tests: several pixels per CTA and multi-pass diagonals on small images)
 static int spatial_cta_cap() {
@@ -569,6 +569,12 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
     CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm->device));
     if (!coop) mode = SP_DIAG;
   }
+  // Measured on B200 (profiles/r02_sweep_modes.txt, spatial stage of a 3-iteration run, wave / ring):
+  //   450x375 ss 35.5 / 43.8 ms, 450x375 S=3 73 / 115, 1242x375 S=3 181 / 232   (<= 2.5 pixels per CTA and diagonal)
+  //   960x540 ss 86 / 83 (3.6), 1920x1080 ss 368 / 216, S=3 781 / 564 (7.3), 3840x2160 ss 1200 / 736 (14.6)
+  // With few pixels per CTA a diagonal is bound by latency, which the wavefront kernel's parallel sums cut; with
+  // many it is bound by instructions per tap and by the serial resolution of near-ties, where the ring wins.
+  if (mode == SP_AUTO) mode = std::min(pm->w, pm->h) <= 3 * sms ? SP_WAVE : SP_RING;
   const int cap = spatial_cta_cap();
   if (mode == SP_WAVE) {
     void (*kern)(PcDev, PmDev, int, unsigned int*, uint8_t*, unsigned long long*, double, int) = nullptr;
@@ -918,6 +924,20 @@ int cspm_debug_taps_executed(unsigned long long* out, int reset) {
       unsigned long long z = 0;
       CSPM_CUDA(cudaMemcpyToSymbol(g_taps_exec, &z, sizeof z));
     }
+  });
+}
+
+int cspm_debug_wave_samples(double* out256, unsigned int* n) {
+  return guard([&] {
+    CSPM_REQUIRE(out256 && n, "null argument");
+    *n = 0;
+#if CSPM_WAVE_PROFILE
+    CSPM_CUDA(cudaDeviceSynchronize());
+    CSPM_CUDA(cudaMemcpyFromSymbol(out256, g_wv_samples, sizeof(double) * 256));
+    CSPM_CUDA(cudaMemcpyFromSymbol(n, g_wv_nsamples, sizeof(unsigned int)));
+    unsigned int z = 0;
+    CSPM_CUDA(cudaMemcpyToSymbol(g_wv_nsamples, &z, sizeof z));
+#endif
   });
 }
 

@@ -57,18 +57,27 @@ constexpr int kWvThreads = CSPM_WAVE_THREADS;
 constexpr int kWvWarps = kWvThreads / 32;
 constexpr int kWvTasks = 32;  // tasks per pass (a CTA owns <= 8 pixels x 2 views per diagonal at HD)
 constexpr int kWvSlots = 4;   // tasks one warp's contiguous run can touch: <= ceil(kWvTasks / kWvWarps) + 2
+constexpr int kWvMaxTaps = 63 * 63;  // wnd_size <= 63 (cspm_pc_create)
 
 struct WvTask {
-  double cand[2][6];       // nx ny nz a b c of the x-axis and the y-axis neighbour
+  double cand[3][6];       // nx ny nz a b c of the x-axis neighbour, the y-axis neighbour, the pixel itself
   double m;                // the pixel's cost at the start of the step (:201,209 compare against it)
   unsigned long long idx;  // y * w + x
   int flags;               // bit0 view, bit1 x-candidate to evaluate, bit2 y-candidate to evaluate
   int x, y, pad_;
 };
+struct WvScale {  // one task at one pyramid level, as GetPlaneCost sees it (pre_cs_pc.cc:139-147,183-185)
+  double abc[3][3];               // disparity plane (a, b, c) of x-candidate, y-candidate, own plane at this scale
+  int cx, cy;                     // centre pixel (x >> s, y >> s)
+  uint32_t Ip;                    // its colour as SAD key
+  int pad_;
+};
 struct WvCtl {
   WvTask task[kWvTasks];
-  double partial[kWvWarps][kWvSlots][2];
-  double strip[kWvWarps][2][64];  // exact path: one window row of addends per candidate
+  WvScale sd[kWvTasks][kMaxScales];
+  double partial[kWvWarps][kWvSlots];  // per warp: tree sum of its share of each candidate evaluation it touched
+  double amb_T[kWvTasks][2];           // tree sums of the undecided tasks
+  double xbuf[2][kWvMaxTaps + 1];  // exact path: every addend of one window, per candidate, row-major
   int amb[kWvTasks];
   int n_amb, pad_[3];
 };
@@ -76,110 +85,41 @@ constexpr size_t kWvSmemBytes = kBulkLutBytes + 16 + sizeof(WvCtl);
 
 // counters of one sweep: {tasks, candidates evaluated, planes adopted on the fast path, tasks sent down the exact path}
 constexpr int kWvStats = 4;
+#if CSPM_WAVE_PROFILE
+__device__ double g_wv_samples[64][4];  // first undecided tasks of the profiled CTA: T0, T1, m, flags
+__device__ unsigned int g_wv_nsamples;
+#endif
 
-struct WvCand {
-  double a, b, c;
-};
-
-// Plane of candidate `p` (six numbers nx ny nz a b c) as GetPlaneCost sees it at scale s (pre_cs_pc.cc:139-147,183-185).
-__device__ __forceinline__ WvCand wave_cand_at_scale(const PcDev& pc, const double p[6], int x, int y, int s, int cx, int cy) {
-  WvCand q;
+// Plane of candidate `p` (six numbers nx ny nz a b c) at scale s, centre (cx, cy).
+__device__ __forceinline__ void wave_cand_at_scale(const PcDev& pc, const double p[6], int x, int y, int s, int cx, int cy,
+                                                   double* a, double* b, double* c) {
   if (!pc.cross_scale) {
-    q.a = p[3]; q.b = p[4]; q.c = p[5];
-    return q;
+    *a = p[3]; *b = p[4]; *c = p[5];
+    return;
   }
   PlaneD pl;
   pl.nx = p[0]; pl.ny = p[1]; pl.nz = p[2]; pl.a = p[3]; pl.b = p[4]; pl.c = p[5];
   double disp = plane_disp(pl, x, y);
   for (int k = 0; k < s; ++k) disp = ddiv(disp, 2.0);
   update_param(pl, (double)cx, (double)cy, disp);
-  q.a = pl.a; q.b = pl.b; q.c = pl.c;
-  return q;
+  *a = pl.a; *b = pl.b; *c = pl.c;
 }
 
-// chunks [ch0, ch0 + nch) of one (task, scale): lane <-> tap ch * 32 + lane in row-major window order
+// addend of window tap k (row-major) of one (task, scale) for the plane (a, b, c); +0.0 outside the image
 template <int CC, int DIR>
-__device__ __forceinline__ void wave_eval_chunks(const TapCtx& tc, const ScaleDev& sc, int cx, int cy, int hw, int wnd, int wtaps,
-                                                 unsigned int magic, int ch0, int nch, uint32_t Ip, bool on0, bool on1,
-                                                 const WvCand& q0, const WvCand& q1, double ws, bool cross, double& acc0,
-                                                 double& acc1) {
-  const int lane = threadIdx.x & 31;
-  CSPM_UNROLL(CSPM_WAVE_UNROLL)
-  for (int ch = ch0; ch < ch0 + nch; ++ch) {
-    const int k = ch * 32 + lane;
-    const int dy = (int)__umulhi((unsigned int)k, magic), dx = k - dy * wnd;
-    const int qx = cx + dx - hw, qy = cy + dy - hw;
-    if (k < wtaps && qx >= 0 && qx < sc.w && qy >= 0 && qy < sc.h) {
-      const int row_off = qy * sc.pitch + sc.pad;
-      uint32_t Iq;
-      double gqp;
-      load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
-      const double wgt = tc.lut_w[__vsadu4(Ip, Iq) << kLutRepShift];
-      const double qyd = (double)qy;
-      if (on0) {
-        const double t = tap_value<CC, DIR>(tc, row_off, qx, Iq, gqp, wgt, q0.a, dadd(dmul(q0.b, qyd), q0.c));
-        acc0 = dadd(acc0, cross ? dmul(t, ws) : t);
-      }
-      if (on1) {
-        const double t = tap_value<CC, DIR>(tc, row_off, qx, Iq, gqp, wgt, q1.a, dadd(dmul(q1.b, qyd), q1.c));
-        acc1 = dadd(acc1, cross ? dmul(t, ws) : t);
-      }
-    }
-  }
+__device__ __forceinline__ double wave_tap(const TapCtx& tc, const ScaleDev& sc, int cx, int cy, uint32_t Ip, double a, double b,
+                                           double c, int hw, int wnd, int wtaps, unsigned int magic, int k) {
+  const int dy = (int)__umulhi((unsigned int)k, magic), dx = k - dy * wnd;
+  const int qx = cx + dx - hw, qy = cy + dy - hw;
+  if (k < wtaps && qx >= 0 && qx < sc.w && qy >= 0 && qy < sc.h)
+    return tap_term<CC, kLutRepShift, DIR>(tc, qy * sc.pitch + sc.pad, qx, Ip, a, dadd(dmul(b, (double)qy), c));
+  return 0.0;
 }
 
 __device__ __forceinline__ double wave_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-}
-
-// Exact GetPlaneCost of both candidates of one task by one warp: lanes compute a window row's addends, lane 0 / 1
-// add the x- / y-candidate's in the reference's order (pre_ss_pc.cc:84-116, pre_cs_pc.cc:151-182).  Returns the
-// candidate's cost in lanes 0 and 1.
-template <int CC>
-__device__ __forceinline__ double wave_exact_pair(const PcDev& pc, const WvTask& T, const double* lut_w, const double* lut_c,
-                                                  double (*strip)[64]) {
-  const int lane = threadIdx.x & 31;
-  const int v = T.flags & 1, hw = pc.half_wnd;
-  const bool on0 = (T.flags & 2) != 0, on1 = (T.flags & 4) != 0;
-  const bool mine = lane == 0 ? on0 : (lane == 1 ? on1 : false);
-  double cost = 0.0;
-  int cx = T.x, cy = T.y;
-  for (int s = 0; s < pc.scale_num; ++s) {
-    const ScaleDev& sc = pc.sc[s];
-    const TapCtx tc = make_tap_ctx(pc, s, v, lut_w, lut_c);
-    const uint32_t Ip = guide_key<CC>(tc.col_v[cy * sc.pitch + sc.pad + cx]);
-    const WvCand q0 = wave_cand_at_scale(pc, T.cand[0], T.x, T.y, s, cx, cy);
-    const WvCand q1 = wave_cand_at_scale(pc, T.cand[1], T.x, T.y, s, cx, cy);
-    const int y0 = max(cy - hw, 0), y1 = min(cy + hw, sc.h - 1), x0 = max(cx - hw, 0), x1 = min(cx + hw, sc.w - 1);
-    const int ncols = x1 - x0 + 1;
-    double sum = 0.0;
-    for (int qy = y0; qy <= y1; ++qy) {
-      const int row_off = qy * sc.pitch + sc.pad;
-      const double qyd = (double)qy;
-      for (int j = lane; j < ncols; j += 32) {
-        const int qx = x0 + j;
-        uint32_t Iq;
-        double gqp;
-        load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
-        const double wgt = tc.lut_w[__vsadu4(Ip, Iq) << kLutRepShift];
-        if (on0) strip[0][j] = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, q0.a, dadd(dmul(q0.b, qyd), q0.c));
-        if (on1) strip[1][j] = tap_value<CC>(tc, row_off, qx, Iq, gqp, wgt, q1.a, dadd(dmul(q1.b, qyd), q1.c));
-      }
-      __syncwarp();
-      if (mine) {
-        const volatile double* sp = strip[lane];
-        for (int j = 0; j < ncols; ++j) sum = dadd(sum, sp[j]);
-      }
-      __syncwarp();
-    }
-    if (pc.cross_scale) cost = dadd(cost, dmul(sum, pc.scale_wgt[s]));  // pre_cs_pc.cc:182
-    else cost = sum;
-    cx /= 2;
-    cy /= 2;
-  }
-  return cost;
 }
 
 template <int CC>
@@ -231,155 +171,297 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + 32 * o) : "memory");
         } while ((int)seen < diag - 1);
       }
+      __syncwarp();
     }
     WV_PROF(0);
     __syncthreads();
     WV_PROF(1);
     for (int base = 0; base < ntasks_mine; base += kWvTasks) {
       const int nt = min(kWvTasks, ntasks_mine - base);
-      // ---------------------------------------------------------------- evaluate: tree sums of all candidates
-      const int total = nt * cpt, per = (total + kWvWarps - 1) / kWvWarps;
-      const int g0 = warp * per, g1 = min(total, g0 + per);
-      const int first_task = g0 < total ? g0 / cpt : 0;
-      int cur_task = -1;
-      double acc0 = 0.0, acc1 = 0.0;
-      // the current task, broadcast to every lane of the warp
-      double c0[6], c1[6];
-      int t_v = 0, t_x = 0, t_y = 0;
-      bool on0 = false, on1 = false;
-      for (int g = g0; g < g1;) {
-        const int task = g / cpt, rem = g - task * cpt, s = rem / cps, ch = rem - s * cps;
-        if (task != cur_task) {
-          if (cur_task >= 0) {
-            const double r0 = wave_warp_sum(acc0), r1 = wave_warp_sum(acc1);
-            if (lane == 0) { ctl->partial[warp][cur_task - first_task][0] = r0; ctl->partial[warp][cur_task - first_task][1] = r1; }
-            acc0 = 0.0; acc1 = 0.0;
-          }
-          cur_task = task;
-          const int tid = 2 * pix0 + base + task;
-          const int u = u_lo + (tid >> 1), t = diag - u;
-          t_v = tid & 1;
-          t_x = rev ? pm.w - 1 - u : u;
-          t_y = rev ? pm.h - 1 - t : t;
-          const size_t idx = (size_t)t_y * pm.w + t_x;
-          on0 = u >= 1;
-          on1 = t >= 1;
-          // lanes 0..5: x-neighbour's plane, 8..13: y-neighbour's, 16..22: own plane and cost.  The neighbours were
-          // written by (possibly) another SM on the previous diagonal: read through L2.
-          const double* st = pm.st[t_v];
-          double val = 0.0;
-          if (lane < 6) { if (on0) val = __ldcg(st + (size_t)lane * n + (idx - inc)); }
-          else if (lane >= 8 && lane < 14) { if (on1) val = __ldcg(st + (size_t)(lane - 8) * n + (idx - (ptrdiff_t)inc * pm.w)); }
-          else if (lane >= 16 && lane < 23) val = __ldcg(st + (size_t)(lane - 16) * n + idx);
-          bool own0 = true, own1 = true, same = true;
+      // ---------------------------------------------------------------- set-up: one warp per task
+      for (int ti = warp; ti < nt; ti += kWvWarps) {
+        const int tid = 2 * pix0 + base + ti;
+        const int u = u_lo + (tid >> 1), t = diag - u;
+        const int t_v = tid & 1;
+        const int t_x = rev ? pm.w - 1 - u : u, t_y = rev ? pm.h - 1 - t : t;
+        const size_t idx = (size_t)t_y * pm.w + t_x;
+        bool on0 = u >= 1, on1 = t >= 1;
+        // lanes 0..5: x-neighbour's plane, 8..13: y-neighbour's, 16..22: own plane and cost.  The neighbours were
+        // written by (possibly) another SM on the previous diagonal: read through L2.
+        const double* st = pm.st[t_v];
+        double val = 0.0;
+        if (lane < 6) { if (on0) val = __ldcg(st + (size_t)lane * n + (idx - inc)); }
+        else if (lane >= 8 && lane < 14) { if (on1) val = __ldcg(st + (size_t)(lane - 8) * n + (idx - (ptrdiff_t)inc * pm.w)); }
+        else if (lane >= 16 && lane < 23) val = __ldcg(st + (size_t)(lane - 16) * n + idx);
+        double c0[6], c1[6], ow[6];
+        bool own0 = true, own1 = true, same = true;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            c0[k] = __shfl_sync(0xffffffffu, val, k);
-            c1[k] = __shfl_sync(0xffffffffu, val, 8 + k);
-            const double o = __shfl_sync(0xffffffffu, val, 16 + k);
-            own0 &= bits_eq(c0[k], o);
-            own1 &= bits_eq(c1[k], o);
-            same &= bits_eq(c0[k], c1[k]);
-          }
-          // exact shortcut 1: a candidate that is bitwise the pixel's own plane re-evaluates to exactly the stored
-          // cost (only while every stored cost is known to be GetPlaneCost of its plane) and cannot pass `<`
-          if (pm.cost_consistent) { on0 = on0 && !own0; on1 = on1 && !own1; }
-          // exact shortcut 2: the y-neighbour carries the x-neighbour's plane: same cost, so after the x-candidate
-          // was tested it can no longer be strictly lower than the minimum
-          if (on0 && on1 && same) on1 = false;
-          if (rem == 0) {  // the warp that owns the task's first chunk files it for the decision phase
-            WvTask& T = ctl->task[task];
-            if (lane < 6) T.cand[0][lane] = val;
-            else if (lane >= 8 && lane < 14) T.cand[1][lane - 8] = val;
-            else if (lane == 22) T.m = val;
-            if (lane == 0) { T.idx = idx; T.flags = t_v | (on0 ? 2 : 0) | (on1 ? 4 : 0); T.x = t_x; T.y = t_y; }
-          }
+        for (int k = 0; k < 6; ++k) {
+          c0[k] = __shfl_sync(0xffffffffu, val, k);
+          c1[k] = __shfl_sync(0xffffffffu, val, 8 + k);
+          ow[k] = __shfl_sync(0xffffffffu, val, 16 + k);
+          own0 &= bits_eq(c0[k], ow[k]);
+          own1 &= bits_eq(c1[k], ow[k]);
+          same &= bits_eq(c0[k], c1[k]);
         }
-        const int nch = min(cps - ch, g1 - g);
-        if (on0 || on1) {
-          const int cx = t_x >> s, cy = t_y >> s;
+        // exact shortcut 1: a candidate that is bitwise the pixel's own plane re-evaluates to exactly the stored
+        // cost (only while every stored cost is known to be GetPlaneCost of its plane) and cannot pass `<`
+        if (pm.cost_consistent) { on0 = on0 && !own0; on1 = on1 && !own1; }
+        // exact shortcut 2: the y-neighbour carries the x-neighbour's plane: same cost, so after the x-candidate
+        // was tested it can no longer be strictly lower than the minimum
+        if (on0 && on1 && same) on1 = false;
+        WvTask& T = ctl->task[ti];
+        if (lane < 6) T.cand[0][lane] = val;
+        else if (lane >= 8 && lane < 14) T.cand[1][lane - 8] = val;
+        else if (lane >= 16 && lane < 22) T.cand[2][lane - 16] = val;
+        else if (lane == 22) T.m = val;
+        if (lane == 0) { T.idx = idx; T.flags = t_v | (on0 ? 2 : 0) | (on1 ? 4 : 0); T.x = t_x; T.y = t_y; }
+        if (lane < S && (on0 || on1)) {  // lane s prepares pyramid level s
+          const int s = lane, cx = t_x >> s, cy = t_y >> s;
+          const ScaleDev& sc = pc.sc[s];
+          WvScale& D = ctl->sd[ti][s];
+          wave_cand_at_scale(pc, c0, t_x, t_y, s, cx, cy, &D.abc[0][0], &D.abc[0][1], &D.abc[0][2]);
+          wave_cand_at_scale(pc, c1, t_x, t_y, s, cx, cy, &D.abc[1][0], &D.abc[1][1], &D.abc[1][2]);
+          wave_cand_at_scale(pc, ow, t_x, t_y, s, cx, cy, &D.abc[2][0], &D.abc[2][1], &D.abc[2][2]);
+          D.cx = cx; D.cy = cy;
+          D.Ip = guide_key<CC>(sc.color[t_v][cy * sc.pitch + sc.pad + cx]);
+        }
+      }
+      __syncthreads();
+      // ---------------------------------------------------------------- evaluate: tree sums of all candidates.
+      // The candidates that survived the shortcuts are numbered 0 .. E-1 (task order, x before y); their
+      // E * cpt chunks of 32 taps are dealt to the warps in contiguous runs, so every warp has the same load
+      // whatever the shortcuts removed.  Every warp derives the numbering from the task flags (lane <-> task).
+      const int my_flags = lane < nt ? ctl->task[lane].flags : 0;
+      const int my_non = ((my_flags >> 1) & 1) + ((my_flags >> 2) & 1);
+      int incl = my_non;  // inclusive prefix over the tasks
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int E = __shfl_sync(0xffffffffu, incl, 31);
+      const int total = E * cpt, per = max(1, (total + kWvWarps - 1) / kWvWarps);
+      const int g0 = warp * per, g1 = min(total, g0 + per);
+      const int first_eval = g0 / cpt;
+      for (int g = g0; g < g1;) {
+        const int e = g / cpt;
+        const int task = __ffs(__ballot_sync(0xffffffffu, incl > e)) - 1;
+        const int excl_t = __shfl_sync(0xffffffffu, incl - my_non, task);
+        const int flags = __shfl_sync(0xffffffffu, my_flags, task);
+        const int cand = (e - excl_t == 0 && (flags & 2)) ? 0 : 1;
+        const int t_v = flags & 1;
+        double acc = 0.0;
+        const int g_end = min(g1, (e + 1) * cpt);
+        while (g < g_end) {
+          const int rem = g - e * cpt, s = rem / cps, ch = rem - s * cps;
+          const int nch = min(cps - ch, g_end - g);
           const ScaleDev& sc = pc.sc[s];
           const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
-          const uint32_t Ip = guide_key<CC>(tc.col_v[cy * sc.pitch + sc.pad + cx]);
-          const WvCand q0 = wave_cand_at_scale(pc, c0, t_x, t_y, s, cx, cy);
-          const WvCand q1 = wave_cand_at_scale(pc, c1, t_x, t_y, s, cx, cy);
+          const WvScale& D = ctl->sd[task][s];
+          const double a = D.abc[cand][0], b = D.abc[cand][1], c = D.abc[cand][2];
+          const int cx = D.cx, cy = D.cy;
+          const uint32_t Ip = D.Ip;
           const double ws = pc.scale_wgt[s];
-          if (t_v == 0) wave_eval_chunks<CC, -1>(tc, sc, cx, cy, hw, wnd, wtaps, magic, ch, nch, Ip, on0, on1, q0, q1, ws, cross, acc0, acc1);
-          else wave_eval_chunks<CC, 1>(tc, sc, cx, cy, hw, wnd, wtaps, magic, ch, nch, Ip, on0, on1, q0, q1, ws, cross, acc0, acc1);
+          if (t_v == 0) {
+            CSPM_UNROLL(CSPM_WAVE_UNROLL)
+            for (int q = ch; q < ch + nch; ++q) {
+              const double tv = wave_tap<CC, -1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, q * 32 + lane);
+              acc = dadd(acc, cross ? dmul(tv, ws) : tv);
+            }
+          } else {
+            CSPM_UNROLL(CSPM_WAVE_UNROLL)
+            for (int q = ch; q < ch + nch; ++q) {
+              const double tv = wave_tap<CC, 1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, q * 32 + lane);
+              acc = dadd(acc, cross ? dmul(tv, ws) : tv);
+            }
+          }
+          g += nch;
         }
-        g += nch;
-      }
-      if (cur_task >= 0) {
-        const double r0 = wave_warp_sum(acc0), r1 = wave_warp_sum(acc1);
-        if (lane == 0) { ctl->partial[warp][cur_task - first_task][0] = r0; ctl->partial[warp][cur_task - first_task][1] = r1; }
+        const double r = wave_warp_sum(acc);
+        if (lane == 0) ctl->partial[warp][e - first_eval] = r;
       }
       WV_PROF(2);
       __syncthreads();
       WV_PROF(3);
       // ---------------------------------------------------------------- decide: certified comparisons
-      if (warp == 0 && lane < nt) {
-        const WvTask& T = ctl->task[lane];
-        const int w_first = (lane * cpt) / per, w_last = ((lane + 1) * cpt - 1) / per;
-        double T0 = 0.0, T1 = 0.0;
-        for (int w = w_first; w <= w_last; ++w) {
-          const int slot = lane - (w * per) / cpt;
-          T0 = dadd(T0, ctl->partial[w][slot][0]);
-          T1 = dadd(T1, ctl->partial[w][slot][1]);
-        }
-        const bool e0 = (T.flags & 2) != 0, e1 = (T.flags & 4) != 0;
-        const double m = T.m;
-        const double lo0 = dmul(T0, dsub(1.0, eps)), hi0 = dmul(T0, dadd(1.0, eps));
-        const double lo1 = dmul(T1, dsub(1.0, eps)), hi1 = dmul(T1, dadd(1.0, eps));
-        int best = -1;
-        bool amb = force_exact && (e0 || e1);
-        double min_lo = m, min_hi = m;
-        if (!amb && e0) {  // x-axis neighbour first (:198-204)
-          if (hi0 < m) { best = 0; min_lo = lo0; min_hi = hi0; }
-          else if (!(lo0 >= m)) amb = true;
-        }
-        if (!amb && e1) {  // then the y-axis neighbour against the updated minimum (:206-212)
-          if (hi1 < min_lo) best = 1;
-          else if (!(lo1 >= min_hi)) amb = true;
-        }
-        st_tasks += 1;
-        st_cands += (e0 ? 1 : 0) + (e1 ? 1 : 0);
-        if (amb) {
-          ctl->amb[atomicAdd(&ctl->n_amb, 1)] = lane;
-          st_exact += 1;
-        } else if (best >= 0) {
-          const int v = T.flags & 1;
-          double* st = pm.st[v];
-          const double* p = T.cand[best];
-          st[T.idx] = p[0]; st[n + T.idx] = p[1]; st[2 * n + T.idx] = p[2];
-          st[3 * n + T.idx] = p[3]; st[4 * n + T.idx] = p[4]; st[5 * n + T.idx] = p[5];
-          st[6 * n + T.idx] = best == 0 ? T0 : T1;  // placeholder until k_cost_fix
-          changed[(size_t)v * n + T.idx] = 1;
-          st_fast += 1;
+      if (warp == 0) {
+        double Tc[2] = {0.0, 0.0};
+        if (lane < nt) {
+          int e = incl - my_non;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (!(my_flags & (2 << c))) continue;
+            const int w_first = (e * cpt) / per, w_last = ((e + 1) * cpt - 1) / per;
+            double tsum = 0.0;
+            for (int w = w_first; w <= w_last; ++w) tsum = dadd(tsum, ctl->partial[w][e - (w * per) / cpt]);
+            Tc[c] = tsum;
+            ++e;
+          }
+          const WvTask& T = ctl->task[lane];
+          const double T0 = Tc[0], T1 = Tc[1];
+          const bool e0 = (my_flags & 2) != 0, e1 = (my_flags & 4) != 0;
+          const double m = T.m;
+          const double lo0 = dmul(T0, dsub(1.0, eps)), hi0 = dmul(T0, dadd(1.0, eps));
+          const double lo1 = dmul(T1, dsub(1.0, eps)), hi1 = dmul(T1, dadd(1.0, eps));
+          int best = -1;
+          bool amb = force_exact && (e0 || e1);
+          double min_lo = m, min_hi = m;
+          if (!amb && e0) {  // x-axis neighbour first (:198-204)
+            if (hi0 < m) { best = 0; min_lo = lo0; min_hi = hi0; }
+            else if (!(lo0 >= m)) amb = true;
+          }
+          if (!amb && e1) {  // then the y-axis neighbour against the updated minimum (:206-212)
+            if (hi1 < min_lo) best = 1;
+            else if (!(lo1 >= min_hi)) amb = true;
+          }
+          st_tasks += 1;
+          st_cands += (e0 ? 1 : 0) + (e1 ? 1 : 0);
+          if (amb) {
+            const int slot = atomicAdd(&ctl->n_amb, 1);
+            ctl->amb[slot] = lane;
+            ctl->amb_T[slot][0] = T0;
+            ctl->amb_T[slot][1] = T1;
+#if CSPM_WAVE_PROFILE
+            if (blockIdx.x == gridDim.x / 2 && !force_exact) {
+              const unsigned int k = atomicAdd(&g_wv_nsamples, 1u);
+              if (k < 64) { g_wv_samples[k][0] = T0; g_wv_samples[k][1] = T1; g_wv_samples[k][2] = m; g_wv_samples[k][3] = (double)T.flags; }
+            }
+#endif
+          } else if (best >= 0) {
+            const int v = T.flags & 1;
+            double* st = pm.st[v];
+            const double* p = T.cand[best];
+            st[T.idx] = p[0]; st[n + T.idx] = p[1]; st[2 * n + T.idx] = p[2];
+            st[3 * n + T.idx] = p[3]; st[4 * n + T.idx] = p[4]; st[5 * n + T.idx] = p[5];
+            st[6 * n + T.idx] = best == 0 ? T0 : T1;  // placeholder until k_cost_fix
+            changed[(size_t)v * n + T.idx] = 1;
+            st_fast += 1;
+          }
         }
       }
       WV_PROF(4);
       __syncthreads();
       WV_PROF(5);
-      // ---------------------------------------------------------------- exact path for the undecided tasks (rare)
+      // ---------------------------------------------------------------- the undecided tasks (near-ties; ~1 %)
+      // Step A — term-wise certificate, all threads: the addends of both candidates AND of the pixel's own plane.
+      // RN addition is monotone, so if candidate addend >= own addend at EVERY tap (every scale), every partial
+      // sum of the candidate's row-major chain is >= the own plane's, hence S_cand >= S_own = m (the stored cost IS
+      // GetPlaneCost of the own plane while cost_consistent): `S_cand < m` is false without summing anything.
+      // Likewise y-candidate >= x-candidate term-wise gives S_1 >= S_0.  This settles the exact ties that make up
+      // most undecided tasks (planes whose partners all lie outside the image cost the same, tap by tap).
+      // Step B — what is still open: lane 0 / 1 of warp 0 add the x- / y-candidate's addends in the reference's
+      // row-major order (pre_ss_pc.cc:84-116, pre_cs_pc.cc:151-182) and the reference's comparison is applied.
       const int n_amb = ctl->n_amb;
-      if (n_amb > 0) {
-        for (int ai = warp; ai < n_amb; ai += kWvWarps) {
-          const WvTask& T = ctl->task[ctl->amb[ai]];
-          const double cst = wave_exact_pair<CC>(pc, T, lut_w, s_lut_c, ctl->strip[warp]);
-          const double s0 = __shfl_sync(0xffffffffu, cst, 0), s1 = __shfl_sync(0xffffffffu, cst, 1);
-          if (lane == 0) {
-            double min_cost = T.m;
-            int best = -1;
-            if ((T.flags & 2) && s0 < min_cost) { min_cost = s0; best = 0; }
-            if ((T.flags & 4) && s1 < min_cost) { min_cost = s1; best = 1; }
-            if (best >= 0) {
-              PlaneD p;
-              const double* c = T.cand[best];
-              p.nx = c[0]; p.ny = c[1]; p.nz = c[2]; p.a = c[3]; p.b = c[4]; p.c = c[5];
-              store_plane(pm.st[T.flags & 1], n, (size_t)T.idx, p, min_cost);
+      for (int ai = 0; ai < n_amb; ++ai) {
+        const int ti = ctl->amb[ai];
+        const WvTask& T = ctl->task[ti];
+        const int flags = T.flags, t_v = flags & 1;
+        const bool on0 = (flags & 2) != 0, on1 = (flags & 4) != 0;
+        bool ge0 = true, ge1o = true, ge10 = true;  // this thread's taps: t0 >= own, t1 >= own, t1 >= t0
+        if (!force_exact) {
+          for (int s = 0; s < S; ++s) {
+            const ScaleDev& sc = pc.sc[s];
+            const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
+            const WvScale& D = ctl->sd[ti][s];
+            for (int k = threadIdx.x; k < wtaps; k += kWvThreads) {
+              const double to = wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[2][0], D.abc[2][1], D.abc[2][2], hw, wnd, wtaps, magic, k);
+              const double t0 = on0 ? wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[0][0], D.abc[0][1], D.abc[0][2], hw, wnd, wtaps, magic, k) : to;
+              const double t1 = on1 ? wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[1][0], D.abc[1][1], D.abc[1][2], hw, wnd, wtaps, magic, k) : to;
+              ge0 = ge0 && t0 >= to;
+              ge1o = ge1o && t1 >= to;
+              ge10 = ge10 && t1 >= t0;
             }
           }
         }
+        const int votes = __syncthreads_and((ge0 ? 1 : 0)) | (__syncthreads_and((ge1o ? 1 : 0)) << 1) | (__syncthreads_and((ge10 ? 1 : 0)) << 2);
+        // the decision with the certificates as extra knowledge (CTA-uniform)
+        const double m = T.m, T0 = ctl->amb_T[ai][0], T1 = ctl->amb_T[ai][1];
+        const bool cert_ok = !force_exact && pm.cost_consistent;
+        int best = -1;
+        bool open_q = force_exact != 0;
+        if (!open_q) {
+          const double lo0 = dmul(T0, dsub(1.0, eps)), hi0 = dmul(T0, dadd(1.0, eps));
+          const double lo1 = dmul(T1, dsub(1.0, eps)), hi1 = dmul(T1, dadd(1.0, eps));
+          bool acc0 = false;
+          if (on0) {
+            if (hi0 < m) acc0 = true;
+            else if (lo0 >= m || (cert_ok && (votes & 1))) acc0 = false;
+            else open_q = true;
+          }
+          if (!open_q && on1) {
+            if (acc0) {  // against S_0
+              if (hi1 < lo0) best = 1;
+              else if (lo1 >= hi0 || (votes & 4)) best = 0;
+              else open_q = true;
+            } else {     // against m
+              if (hi1 < m) best = 1;
+              else if (lo1 >= m || (cert_ok && (votes & 2))) best = -1;
+              else open_q = true;
+            }
+          } else if (!open_q && acc0) best = 0;
+        }
+        if (!open_q) {
+          if (best >= 0 && threadIdx.x == 0) {
+            double* st = pm.st[t_v];
+            const double* p = T.cand[best];
+            st[T.idx] = p[0]; st[n + T.idx] = p[1]; st[2 * n + T.idx] = p[2];
+            st[3 * n + T.idx] = p[3]; st[4 * n + T.idx] = p[4]; st[5 * n + T.idx] = p[5];
+            st[6 * n + T.idx] = best == 0 ? T0 : T1;  // placeholder until k_cost_fix
+            changed[(size_t)t_v * n + T.idx] = 1;
+          }
+          continue;
+        }
+        // Step B
+        double cost = 0.0;  // lane 0 / 1 of warp 0: the candidate's running cost over the scales
+        for (int s = 0; s < S; ++s) {
+          const ScaleDev& sc = pc.sc[s];
+          const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
+          const WvScale& D = ctl->sd[ti][s];
+          for (int k = threadIdx.x; k < wtaps; k += kWvThreads) {
+            ctl->xbuf[0][k] = on0 ? wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[0][0], D.abc[0][1], D.abc[0][2], hw, wnd, wtaps, magic, k) : 0.0;
+            ctl->xbuf[1][k] = on1 ? wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[1][0], D.abc[1][1], D.abc[1][2], hw, wnd, wtaps, magic, k) : 0.0;
+          }
+          __syncthreads();
+          if (warp == 0 && lane < 2 && (lane == 0 ? on0 : on1)) {
+            const int y0 = max(D.cy - hw, 0), y1 = min(D.cy + hw, sc.h - 1), x0 = max(D.cx - hw, 0), x1 = min(D.cx + hw, sc.w - 1);
+            const volatile double* xb = ctl->xbuf[lane];
+            double sum = 0.0;
+            for (int qy = y0; qy <= y1; ++qy) {
+              const volatile double* row = xb + (qy - D.cy + hw) * wnd + (x0 - D.cx + hw);
+              const int nc = x1 - x0 + 1;
+              int j = 0;
+              for (; j + 8 <= nc; j += 8) {  // 8 loads in flight, then 8 dependent adds
+                double t[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = row[j + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sum = dadd(sum, t[q]);
+              }
+              for (; j < nc; ++j) sum = dadd(sum, row[j]);
+            }
+            cost = cross ? dadd(cost, dmul(sum, pc.scale_wgt[s])) : sum;  // pre_cs_pc.cc:182
+          }
+          __syncthreads();
+        }
+        if (warp == 0) {
+          const double s0 = __shfl_sync(0xffffffffu, cost, 0), s1 = __shfl_sync(0xffffffffu, cost, 1);
+          if (lane == 0) {
+            double min_cost = m;
+            int bb = -1;
+            if (on0 && s0 < min_cost) { min_cost = s0; bb = 0; }
+            if (on1 && s1 < min_cost) { min_cost = s1; bb = 1; }
+            if (bb >= 0) {
+              PlaneD p;
+              const double* c = T.cand[bb];
+              p.nx = c[0]; p.ny = c[1]; p.nz = c[2]; p.a = c[3]; p.b = c[4]; p.c = c[5];
+              store_plane(pm.st[t_v], n, (size_t)T.idx, p, min_cost);
+            }
+            st_exact += 1;
+          }
+        }
+      }
+      if (n_amb > 0) {
         __syncthreads();
         if (threadIdx.x == 0) ctl->n_amb = 0;
       }

@@ -202,6 +202,9 @@ int cspm_debug_counters(unsigned long long* out8, int reset);
  * refinement, cost fix-up) actually EXECUTED on the current device since the last reset — the nominal count
  * minus what exact early termination skipped. */
 int cspm_debug_taps_executed(unsigned long long* out, int reset);
+/* Diagnostic builds (-DCSPM_WAVE_PROFILE=1) only (n = 0 otherwise): {T0, T1, m, flags} of the first <= 64 tasks one
+ * CTA of the wavefront sweep could not decide from its tree sums (n = how many it met); out256[64 * 4]. */
+int cspm_debug_wave_samples(double* out256, unsigned int* n);
 /* Diagnostic builds (-DCSPM_PROFILE_LANES=1) only, zeros otherwise: out33[k] = window rows the bulk kernels
  * executed with k of a warp's 32 lanes still evaluating (per-lane early termination leaves the others idle). */
 int cspm_debug_lane_hist(unsigned long long* out33, int reset);

@@ -20,3 +20,10 @@ for it in range(2):
     names = ["nbr_wait", "bar1", "eval_w0", "wait_slowest_warp", "decide", "bar3", "publish"]
     print(f"{w}x{h}x{d} {'cs' if cs else 'ss'} sweep {it}: {dt*1e3:.1f} ms wall (incl. fix-up), {nd} diagonals, {dt*1e6/nd:.1f} us/diag; mid-CTA cycles/diag:",
           {k: round(v / nd) for k, v in zip(names, out)}, "total", round(sum(out[:7]) / nd), pm.stats(), flush=True)
+    smp = (C.c_double * 256)(); ns = C.c_uint32(0)
+    c._lib.dll.cspm_debug_wave_samples(smp, C.byref(ns))
+    print(f"  undecided tasks met by the profiled CTA: {ns.value}; first ones (T0, T1, m, flags, (T0-m)/m, (T1-m)/m, (T1-T0)/T0):")
+    for k in range(min(ns.value, 24)):
+        T0, T1, m, fl = smp[4 * k:4 * k + 4]
+        rel = lambda a, b: (a - b) / b if b else float("nan")
+        print(f"    {T0!r:>24} {T1!r:>24} {m!r:>24} {int(fl)} {rel(T0, m):.3e} {rel(T1, m):.3e} {rel(T1, T0):.3e}")

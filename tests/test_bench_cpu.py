@@ -19,6 +19,8 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "sample" in d["cpu_baseline"]
+    assert d["product_so_loaded"] is False, "the reference arm must not map libcspm_b200.so"
+    assert d["cpu_baseline"]["sample_kind"] in ("crop", "full") and "build" in d["cpu_baseline"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
