@@ -44,9 +44,20 @@
 
 namespace cspm {
 
+// -DCSPM_LUTC_REP=0: colour table not replicated in the bulk layout (round-1 layout)
+#ifndef CSPM_LUTC_REP
+#define CSPM_LUTC_REP 1
+#endif
 constexpr int kMaxScales = 8;
 constexpr int kLutW = 1000;   // exp(-i/10) table, pre_ss_pc.cc:61-64
 constexpr int kLutC = 32;     // colour term table: 0.1*min(k*0.3333333333,10), saturates at k>=31
+constexpr int kLutWUsed = 766;      // reachable weight-table entries: L1 distance of two 8-bit BGR pixels <= 765
+constexpr int kLutRepShift = 4;     // bulk layout: tables replicated 16x, one copy per lane mod 16
+constexpr int kLutCRepShift = CSPM_LUTC_REP ? kLutRepShift : 0;
+// Bulk layout of the dynamic shared memory (doubles): [weight table x16][colour table x16 | x1][mbarrier][strips]
+constexpr int kBulkLutCOff = kLutWUsed << kLutRepShift;
+constexpr int kBulkMbarOff = kBulkLutCOff + (kLutC << kLutCRepShift);
+constexpr int kBulkCoopOff = kBulkMbarOff + 2;
 constexpr double kDoubleEps = 0.00000001;  // commfunc.h:26
 
 // Raw cost behind the window sum: GrdCC / CenCC volumes (PreSSPC, PreCSPC) or the image-interpolating
@@ -250,11 +261,14 @@ __device__ __forceinline__ double abs_min_2p28(double x) {
 // formed as min(|k * dG|, k * TAU_GRD): multiplication by k > 0 is monotone under round-to-nearest and
 // commutes with |.|, so both sides of the min are the correctly rounded products the reference computes in
 // either case — and the absolute value rides as an operand modifier on the final add (one FP64 op less).
+// LCS: log2 of the replication factor of the colour table (bulk layout: one copy per lane mod 16, like the weight
+// table, so that the data-dependent 64-bit lookups of a half-warp never share a bank pair)
+template <int LCS = 0>
 __device__ __forceinline__ double raw_cost_cg(const unsigned long long* cg_o, const double* lut_c, double k_grd27,
                                               uint32_t exp_hi, int idx, uint32_t kq, double gq) {
   const CgPix p = cg_load(cg_o, idx, exp_hi);
   const int sad = min((int)__vsadu4(kq, p.key), kLutC - 1);
-  const double clr = lut_c[sad];                          // ALPHA * min(sum*0.3333333333, TAU_CLR)
+  const double clr = lut_c[sad << LCS];                   // ALPHA * min(sum*0.3333333333, TAU_CLR)
   const double kd = dmul(k_grd27, dsub(gq, p.g));         // (1-ALPHA) * (lG-rG), signed
   const double k_tau = dmul(k_grd27, 268435456.0);        // (1-ALPHA) * TAU_GRD (exact power-of-two scaling)
   const double grd = fabs(kd) > k_tau ? k_tau : kd;
@@ -298,7 +312,7 @@ struct TapCtx {
 // DIR: the view's partner direction when known at compile time (-1 left view, +1 right view), 0 = read t.raw.dir.
 // ALLVALID: the caller has proved that trunc(q_disp) lies in [1, max_disp) for every tap of the window
 // (GRD only): the validity test and the max_cost select are compiled out.
-template <int CC, int DIR = 0, bool ALLVALID = false>
+template <int CC, int DIR = 0, bool ALLVALID = false, int LCS = 0>
 __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
                                                double q_disp) {
   const int fl = __double2int_rz(q_disp);  // static_cast<int>: truncation toward zero
@@ -312,8 +326,8 @@ __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int
     const double fw = dsub((double)(flc + 1), q_disp);
     const int dir = DIR != 0 ? DIR : t.raw.dir;  // compile-time: the second partner load is the first +- 8 bytes
     const int i0 = row_off + qx + dir * flc;
-    const double c0 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0, Iq, gqp);
-    const double c1 = raw_cost_cg(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0 + dir, Iq, gqp);
+    const double c0 = raw_cost_cg<LCS>(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0, Iq, gqp);
+    const double c1 = raw_cost_cg<LCS>(t.raw.cg_o, t.raw.lut_c, t.raw.k_grd27, t.raw.cg_exp_hi, i0 + dir, Iq, gqp);
     const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
     return dmul(wgt, ALLVALID ? tmp : (valid ? tmp : t.max_cost));
   }
@@ -349,10 +363,10 @@ __device__ __forceinline__ double tap_value_qd(const TapCtx& t, int row_off, int
   const double tmp = dadd(dmul(fw, c0), dmul(dsub(1.0, fw), c1));
   return dmul(wgt, tmp);
 }
-template <int CC, int DIR = 0, bool ALLVALID = false>
+template <int CC, int DIR = 0, bool ALLVALID = false, int LCS = 0>
 __device__ __forceinline__ double tap_value(const TapCtx& t, int row_off, int qx, uint32_t Iq, double gqp, double wgt,
                                             double a, double q_disp_y) {
-  return tap_value_qd<CC, DIR, ALLVALID>(t, row_off, qx, Iq, gqp, wgt, dadd(dmul(a, (double)qx), q_disp_y));
+  return tap_value_qd<CC, DIR, ALLVALID, LCS>(t, row_off, qx, Iq, gqp, wgt, dadd(dmul(a, (double)qx), q_disp_y));
 }
 // Guide pixel q of this view.  GRD: the SAD key and the gradient double of the packed word (centre colours
 // compared against it must go through guide_key); other kinds: the plain packed colour.
@@ -379,7 +393,7 @@ __device__ __forceinline__ double tap_term(const TapCtx& t, int row_off, int qx,
   double gqp;
   load_guide<CC>(t, row_off + qx, &Iq, &gqp);
   const double wgt = t.lut_w[__vsadu4(Ip, Iq) << LWS];
-  return tap_value<CC, DIR, ALLVALID>(t, row_off, qx, Iq, gqp, wgt, a, q_disp_y);
+  return tap_value<CC, DIR, ALLVALID, (LWS > 0 ? kLutCRepShift : 0)>(t, row_off, qx, Iq, gqp, wgt, a, q_disp_y);
 }
 
 __device__ __forceinline__ TapCtx make_tap_ctx(const PcDev& pc, int s, int v, const double* lut_w,
@@ -572,7 +586,7 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
     }
     const bool all_ok = __all_sync(__activemask(), ok);
     // per-warp strip for the cooperative tail: behind the colour table and the mbarrier of the bulk layout
-    double* coop = COOP ? const_cast<double*>(lut_c) + kLutC + 2 + (size_t)threadIdx.y * kCoopStride : nullptr;
+    double* coop = COOP ? const_cast<double*>(lut_w) - (threadIdx.x & 15) + kBulkCoopOff + (size_t)threadIdx.y * kCoopStride : nullptr;
     if (all_ok)
       return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
                     : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
@@ -618,9 +632,12 @@ __device__ __forceinline__ void stage_luts(const PcDev& pc, double* s_lut_w, dou
 // Bulk (thread-per-pixel) kernels: weight table replicated 16x, one copy per lane-mod-16, so that the
 // 64-bit data-dependent lookups of a half-warp always hit 16 different bank pairs.  Only the 766
 // reachable entries (L1 distance of two 8-bit BGR pixels <= 765) are staged: 98 KB.
-constexpr int kLutWUsed = 766;
-constexpr int kLutRepShift = 4;
-constexpr size_t kBulkLutBytes = sizeof(double) * ((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);  // 98 304 B, multiple of 16
+constexpr size_t kBulkLutBytes = sizeof(double) * (size_t)kBulkMbarOff;  // 102 144 B (98 304 un-replicated), multiple of 16
+__device__ __forceinline__ const double* bulk_lut_w(const double* s_dyn) { return s_dyn + (threadIdx.x & 15); }
+__device__ __forceinline__ const double* bulk_lut_c(const double* s_dyn) {
+  return s_dyn + kBulkLutCOff + (kLutCRepShift ? (threadIdx.x & 15) : 0);
+}
+__device__ __forceinline__ unsigned long long* bulk_mbar(double* s_dyn) { return reinterpret_cast<unsigned long long*>(s_dyn + kBulkMbarOff); }
 constexpr int kBulkWarpsMax = CSPM_BULK_BY > CSPM_BULK_BY_CS ? CSPM_BULK_BY : CSPM_BULK_BY_CS;
 // + the mbarrier + one cooperative-tail strip per warp (126 KB with 24 warps: still the 132 KB carve-out)
 constexpr size_t kBulkSmemBytes = kBulkLutBytes + 16 + (size_t)kBulkWarpsMax * kCoopStride * sizeof(double);

@@ -54,10 +54,10 @@ constexpr int kBulkMinB = CSPM_BULK_MINB;  // CTAs per SM the register allocatio
 template <int CC, bool CS>
 __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_init(PcDev pc, PmDev pm) {
   extern __shared__ __align__(16) double s_dyn[];
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
-  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const double* s_lut_w = bulk_lut_w(s_dyn);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int v = blockIdx.z;
@@ -81,10 +81,10 @@ __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_init(PcDev pc
 template <int CC, bool CS>
 __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
   extern __shared__ __align__(16) double s_dyn[];
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
-  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const double* s_lut_w = bulk_lut_w(s_dyn);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int v = blockIdx.z;
@@ -132,10 +132,10 @@ __device__ __forceinline__ bool plane_bits_eq(const PlaneD& p, const PlaneD& q) 
 template <int CC, bool CS>
 __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_redblack(PcDev pc, PmDev pm, int colour, int noff) {
   extern __shared__ __align__(16) double s_dyn[];
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);
-  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const double* s_lut_w = bulk_lut_w(s_dyn);
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x) + ((y + colour) & 1);
   const int v = blockIdx.z;
@@ -281,10 +281,10 @@ template <int CC, bool CS>
 __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_view_eval(PcDev pc, PmDev pm, int v, double* cand_cost, int* cand_tx,
                                                    unsigned long long* tmin, unsigned long long* tap_counter) {
   extern __shared__ __align__(16) double s_dyn[];
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);  // TMA bulk copy in flight while the candidate is drawn
-  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const double* s_lut_w = bulk_lut_w(s_dyn);
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   unsigned long long taps = 0;

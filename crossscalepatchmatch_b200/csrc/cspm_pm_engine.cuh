@@ -21,6 +21,20 @@
 #ifndef CSPM_SPATIAL_DEDUP
 #define CSPM_SPATIAL_DEDUP 1
 #endif
+// Neighbour-progress poll of the persistent sweeps.  ld.acquire.gpu compiles to LDG.STRONG.GPU + CCTL.IVALL, i.e.
+// every poll iteration invalidates the SM's L1.  A relaxed poll (-DCSPM_SP_ACQUIRE_POLL=0) would be enough in
+// practice — the only data another CTA writes during the kernel is the plane state, which is read exclusively
+// with ld.global.cg (LDG.STRONG.GPU, served by L2), and L1 only holds the immutable images — but it was measured
+// to buy 1 % of the sweep at most (HD ring 212.5 vs 215.4 ms, 450x375 wavefront 34.6 vs 35.3 ms), so the
+// formally synchronising acquire stays the default.
+#ifndef CSPM_SP_ACQUIRE_POLL
+#define CSPM_SP_ACQUIRE_POLL 1
+#endif
+#if CSPM_SP_ACQUIRE_POLL
+#define CSPM_SP_POLL(dst, ptr) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dst) : "l"(ptr) : "memory")
+#else
+#define CSPM_SP_POLL(dst, ptr) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(dst) : "l"(ptr) : "memory")
+#endif
 __device__ __forceinline__ bool bits_eq(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 
 constexpr int kSpThreads = CSPM_SP_THREADS;
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(kSpThreads, kSpCtasPerSm) k_spatial_persist(Pc
       for (int o = o_lo + lane; o <= o_hi; o += 32) {
         unsigned int seen;
         do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(barrier_ctr + 32 * o) : "memory");
+          CSPM_SP_POLL(seen, barrier_ctr + 32 * o);
         } while ((int)seen < diag - 1);
       }
 #if !CSPM_SP_LEANFENCE

@@ -126,12 +126,12 @@ template <int CC>
 __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev pm, int rev, unsigned int* progress, uint8_t* changed,
                                                                 unsigned long long* wstats, double eps, int force_exact) {
   extern __shared__ __align__(16) double s_dyn[];
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   WvCtl* ctl = reinterpret_cast<WvCtl*>(s_mbar + 2);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double* lut_w = s_dyn + (lane & 15);  // this lane's copy of the 16x replicated weight table
+  const double* lut_w = bulk_lut_w(s_dyn);  // this lane's copy of the 16x replicated weight table
   const size_t n = (size_t)pm.w * pm.h;
   const int inc = rev ? -1 : 1;
   const int hw = pc.half_wnd, wnd = 2 * hw + 1, wtaps = wnd * wnd;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
       for (int o = o_lo + lane; o <= o_hi; o += 32) {
         unsigned int seen;
         do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress + 32 * o) : "memory");
+          CSPM_SP_POLL(seen, progress + 32 * o);
         } while ((int)seen < diag - 1);
       }
       __syncwarp();
@@ -517,10 +517,10 @@ __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_cost_fix(PcDe
   const int v = blockIdx.y;
   const unsigned int cnt = count[v];
   if (blockIdx.x * kCta >= cnt) return;  // CTA-uniform, before the bulk copy is issued
-  double* s_lut_c = s_dyn + (size_t)kLutWUsed * (1 << kLutRepShift);
-  unsigned long long* s_mbar = reinterpret_cast<unsigned long long*>(s_lut_c + kLutC);
+  const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
+  unsigned long long* s_mbar = bulk_mbar(s_dyn);
   tma_stage_luts_begin(pc, s_dyn, s_mbar);
-  const double* s_lut_w = s_dyn + (threadIdx.x & 15);
+  const double* s_lut_w = bulk_lut_w(s_dyn);
   const unsigned int slot = blockIdx.x * kCta + threadIdx.y * 32 + threadIdx.x;
   tma_stage_luts_wait(s_mbar);
   if (slot >= cnt) return;

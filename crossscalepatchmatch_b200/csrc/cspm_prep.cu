@@ -402,10 +402,11 @@ static cspm_pc* pc_create(const uint8_t* l, const uint8_t* r, bool on_device, in
     D.lut_w = d_lut_w;
     D.lut_c = d_lut_c;
     {  // 16x replicated weight table + colour table, contiguous, for the bulk kernels' single TMA bulk copy
-      std::vector<double> rep((size_t)kLutWUsed * (1 << kLutRepShift) + kLutC);
+      std::vector<double> rep((size_t)kBulkMbarOff);
       for (int i = 0; i < kLutWUsed; ++i)
         for (int r = 0; r < (1 << kLutRepShift); ++r) rep[((size_t)i << kLutRepShift) + r] = lut_w[i];
-      for (int k = 0; k < kLutC; ++k) rep[(size_t)kLutWUsed * (1 << kLutRepShift) + k] = lut_c[k];
+      for (int k = 0; k < kLutC; ++k)
+        for (int r = 0; r < (1 << kLutCRepShift); ++r) rep[(size_t)kBulkLutCOff + ((size_t)k << kLutCRepShift) + r] = lut_c[k];
       double* d_rep = pc->arena.alloc<double>(rep.size());
       CSPM_CUDA(cudaMemcpyAsync(d_rep, rep.data(), sizeof(double) * rep.size(), cudaMemcpyHostToDevice, st));
       CSPM_CUDA(cudaStreamSynchronize(st));
