@@ -116,6 +116,58 @@ __device__ __forceinline__ double wave_tap(const TapCtx& tc, const ScaleDev& sc,
   return 0.0;
 }
 
+// Chunks [ch, ch + nch) of one (candidate, scale), accumulated into this lane's partial sum.  For windows at least
+// a warp wide (the reference's 35), chunk q < wnd is window ROW q with lane <-> column (columns 0..31): the column
+// test, a * q_x and the pointers are per-lane constants of the whole segment and the row part of the disparity is
+// warp-uniform, which saves a third of the instructions of the linear mapping; the remaining wnd - 32 columns of all
+// rows follow as (wnd - 32) * wnd / 32 linear chunks.  The number of chunks, ceil(wnd^2 / 32), is the same either
+// way.  Any order is fine here: these are the tree sums (the exact paths index taps linearly, wave_tap).
+template <int CC, int DIR>
+__device__ __forceinline__ double wave_eval_segment(const TapCtx& tc, const ScaleDev& sc, int cx, int cy, uint32_t Ip, double a,
+                                                    double b, double c, int hw, int wnd, int wtaps, unsigned int magic, int ch,
+                                                    int nch, double ws, bool cross, double acc) {
+  const int lane = threadIdx.x & 31;
+  if (wnd < 32) {
+    CSPM_UNROLL(CSPM_WAVE_UNROLL)
+    for (int q = ch; q < ch + nch; ++q) {
+      const double tv = wave_tap<CC, DIR>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, q * 32 + lane);
+      acc = dadd(acc, cross ? dmul(tv, ws) : tv);
+    }
+    return acc;
+  }
+  const int sw = sc.w, sh = sc.h, pitch = sc.pitch, pad = sc.pad;
+  const int qx = cx - hw + lane;
+  const bool in_x = qx >= 0 && qx < sw;
+  const double ax = dmul(a, (double)qx);
+  const int rows_end = min(ch + nch, wnd);
+  CSPM_UNROLL(CSPM_WAVE_UNROLL)
+  for (int q = ch; q < rows_end; ++q) {
+    const int qy = cy - hw + q;
+    if (in_x && qy >= 0 && qy < sh) {
+      const int row_off = qy * pitch + pad;
+      uint32_t Iq;
+      double gqp;
+      load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
+      const double wgt = tc.lut_w[__vsadu4(Ip, Iq) << kLutRepShift];
+      const double tv = tap_value_qd<CC, DIR, false, kLutCRepShift>(tc, row_off, qx, Iq, gqp, wgt, dadd(ax, dadd(dmul(b, (double)qy), c)));
+      acc = dadd(acc, cross ? dmul(tv, ws) : tv);
+    }
+  }
+  const int remc = wnd - 32, nrem = remc * wnd;
+  for (int q = max(ch, wnd); q < ch + nch; ++q) {
+    const int r = (q - wnd) * 32 + lane;
+    if (r < nrem) {
+      const int dy = r / remc, dx = 32 + r - dy * remc;
+      const int rx = cx - hw + dx, ry = cy - hw + dy;
+      if (rx >= 0 && rx < sw && ry >= 0 && ry < sh) {
+        const double tv = tap_term<CC, kLutRepShift, DIR>(tc, ry * pitch + pad, rx, Ip, a, dadd(dmul(b, (double)ry), c));
+        acc = dadd(acc, cross ? dmul(tv, ws) : tv);
+      }
+    }
+  }
+  return acc;
+}
+
 __device__ __forceinline__ double wave_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -263,19 +315,8 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
           const int cx = D.cx, cy = D.cy;
           const uint32_t Ip = D.Ip;
           const double ws = pc.scale_wgt[s];
-          if (t_v == 0) {
-            CSPM_UNROLL(CSPM_WAVE_UNROLL)
-            for (int q = ch; q < ch + nch; ++q) {
-              const double tv = wave_tap<CC, -1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, q * 32 + lane);
-              acc = dadd(acc, cross ? dmul(tv, ws) : tv);
-            }
-          } else {
-            CSPM_UNROLL(CSPM_WAVE_UNROLL)
-            for (int q = ch; q < ch + nch; ++q) {
-              const double tv = wave_tap<CC, 1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, q * 32 + lane);
-              acc = dadd(acc, cross ? dmul(tv, ws) : tv);
-            }
-          }
+          if (t_v == 0) acc = wave_eval_segment<CC, -1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, ch, nch, ws, cross, acc);
+          else acc = wave_eval_segment<CC, 1>(tc, sc, cx, cy, Ip, a, b, c, hw, wnd, wtaps, magic, ch, nch, ws, cross, acc);
           g += nch;
         }
         const double r = wave_warp_sum(acc);

@@ -1,5 +1,5 @@
 """Profiling driver: exactly one device-resident step (the bench.py step_device
-body) so ncu sees one pass of the hot path.  usage: run_one_step.py [WxHxD] [cs]"""
+body) so ncu sees one pass of the hot path.  usage: run_one_step.py [WxHxD] [ss|cs] [schedule 0|1|2]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,7 +15,8 @@ c.set_thread_stream(torch.cuda.current_stream().cuda_stream)
 cc = c.GetCCType("GRD")
 ptrs = ((dl.data_ptr(), w, h, 3 * w), (dr.data_ptr(), w, h, 3 * w))
 pc = c.PreCSPC(None, None, d, 35, 3, cc, 0.3, device_ptrs=ptrs) if cs else c.PreSSPC(None, None, d, 35, cc, device_ptrs=ptrs)
-pm = c.CSPatchMatch(None, None, d, 1, device_ptrs=ptrs)
+schedule = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+pm = c.CSPatchMatch(None, None, d, 1, device_ptrs=ptrs, schedule=schedule)
 pm.PatchMatch(3, pc, False)
 torch.cuda.synchronize()
 print("stage_ms", pm.stage_ms(), pm.stats())
