@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--cpu-full", action="store_true", help="CPU arm on the whole image instead of the bounded crop (BASELINE.md table)")
     ap.add_argument("--schedule", type=int, default=0, choices=[0, 1, 2],
                     help="0 raster = the reference's order (headline), 1 / 2 red-black with 4 / 8 neighbours (throughput schedules)")
+    ap.add_argument("--pairs-in-flight", type=int, default=1,
+                    help="throughput mode: a step is a batch of P independent pairs per GPU (cspm_pm_patchmatch_batch: their "
+                         "spatial sweeps share one launch); the headline is P = 1")
     ap.add_argument("--no-worst-case", action="store_true", help="skip the extra step with early termination disabled")
     ap.add_argument("--no-tap-count", action="store_true", help="skip the executed-tap count (instrumented build)")
     return ap.parse_args()
@@ -275,11 +278,15 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     w, h, d, name = workload(args)
 
-    # this rank's pair (config C4 seed + pair index); pinned host copies for the e2e leg
-    l, r, _ = make_pair(w, h, d, SEED_BASE + 3 + rank)
-    hl = torch.from_numpy(l).pin_memory()
-    hr = torch.from_numpy(r).pin_memory()
-    dl, dr = hl.to(dev), hr.to(dev)
+    # this rank's pairs (config C4 seed + pair index; P > 1: P distinct pairs); pinned host copies for the e2e leg
+    P = max(1, args.pairs_in_flight)
+    host, devp = [], []
+    for k in range(P):
+        l, r, _ = make_pair(w, h, d, SEED_BASE + 3 + rank + 1000 * k)
+        hl = torch.from_numpy(l).pin_memory()
+        hr = torch.from_numpy(r).pin_memory()
+        host.append((hl, hr))
+        devp.append((hl.to(dev), hr.to(dev)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     stream = torch.cuda.current_stream()
@@ -301,21 +308,28 @@ def run_b200(args):
     launches = {"n": 0}
     last = {}
 
+    def run_pairs(pms, pcs):
+        if P == 1:
+            pms[0].PatchMatch(ITERS, pcs[0], False)
+        else:
+            c.PatchMatchBatch(pms, pcs, ITERS, False)
+
     def step_device():
-        """reference's timed region with inputs resident in HBM"""
-        pc = make_pc(dl, dr, True)
-        pm = c.CSPatchMatch(None, None, d, 1, seed=PM_SEED, device=local, schedule=args.schedule,
-                            device_ptrs=((dl.data_ptr(), w, h, 3 * w), (dr.data_ptr(), w, h, 3 * w)))
-        pm.PatchMatch(ITERS, pc, False)
-        launches["n"] += pc.stats()["kernel_launches"] + pm.stats()["kernel_launches"]
-        last.update(stage_ms=pm.stage_ms(), taps_eval=pc.taps_per_image_eval(), n_ref=pm.n_ref(), stats=pm.stats())
-        return pc, pm
+        """reference's timed region with inputs resident in HBM (P pairs: the region once per pair, batched)"""
+        pcs = [make_pc(dl, dr, True) for dl, dr in devp]
+        pms = [c.CSPatchMatch(None, None, d, 1, seed=PM_SEED, device=local, schedule=args.schedule,
+                              device_ptrs=((dl.data_ptr(), w, h, 3 * w), (dr.data_ptr(), w, h, 3 * w))) for dl, dr in devp]
+        run_pairs(pms, pcs)
+        launches["n"] += sum(pc.stats()["kernel_launches"] for pc in pcs) + sum(pm.stats()["kernel_launches"] for pm in pms)
+        st = {k: sum(pm.stats()[k] for pm in pms) for k in pms[0].stats()}
+        last.update(stage_ms=[v / P for v in pms[0].stage_ms()], taps_eval=pcs[0].taps_per_image_eval(), n_ref=pms[0].n_ref(), stats=st)
+        return pcs, pms
 
     def step_e2e():
-        pc = make_pc(hl, hr, False)
-        pm = c.CSPatchMatch(hl.numpy(), hr.numpy(), d, 1, seed=PM_SEED, device=local, schedule=args.schedule)
-        pm.PatchMatch(ITERS, pc, False)
-        return pm.dis(c.kLeft), pm.dis(c.kRight)
+        pcs = [make_pc(hl, hr, False) for hl, hr in host]
+        pms = [c.CSPatchMatch(hl.numpy(), hr.numpy(), d, 1, seed=PM_SEED, device=local, schedule=args.schedule) for hl, hr in host]
+        run_pairs(pms, pcs)
+        return [(pm.dis(c.kLeft), pm.dis(c.kRight)) for pm in pms]
 
     def barrier():
         if world > 1:
@@ -355,7 +369,7 @@ def run_b200(args):
 
     from crossscalepatchmatch_b200 import shard
 
-    units, (t_dev, t_e2e) = shard.aggregate(float(w * h * d * args.steps), [t_dev, t_e2e], device=dev)
+    units, (t_dev, t_e2e) = shard.aggregate(float(w * h * d * args.steps * P), [t_dev, t_e2e], device=dev)
     gpu_launches, _ = shard.aggregate(float(gpu_launches), [0.0], device=dev)  # whole job: summed over ranks
 
     if rank == 0:
@@ -402,19 +416,20 @@ def run_b200(args):
             "metric": "Mpixel*disparities/s", "value": value, "unit": "Mpixel*disp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "pairs_per_gpu_per_step": 1, "sharding": "one stereo pair per GPU, no data-path collective",
+            "config": {"workload": name, "pairs_per_gpu_per_step": P, "pairs_in_flight": P, "sharding": "one stereo pair per GPU, no data-path collective",
                        "schedule": SCHEDULE_NAMES[args.schedule] + (" (bit-exact reference order)" if args.schedule == 0 else " (throughput schedule, not the reference's order)"),
                        "l2": "flushed between timed steps (256 MiB write)"},
-            "e2e": {"value": e2e, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 4 * w * h * 3, "d2h_bytes_per_step": 2 * w * h,
+            "e2e": {"value": e2e, "unit": "Mpixel*disp/s", "h2d_bytes_per_step": 4 * w * h * 3 * P, "d2h_bytes_per_step": 2 * w * h * P,
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": roofline,
             "stage_ms": stage_ms,
             "window_taps_per_step": int(last["stats"]["window_taps"]),
+            "stage_ms_note": "per pair (batch totals / pairs_in_flight)" if P > 1 else "one pair",
             "spatial_sweep": {k: int(last["stats"][k]) for k in ("spatial_tasks", "spatial_candidates", "spatial_adopted", "spatial_exact_tasks")},
         }
-        if world == 1 and not args.no_worst_case:
+        if world == 1 and not args.no_worst_case and P == 1:
             # data-independent figure: the same step with exact early termination switched off (every window summed in full)
             os.environ["CSPM_NO_EARLY_TERM"] = "1"
             step_device()

@@ -8,7 +8,7 @@ fails loudly if the shared object is missing (there is no CPU fallback)."""
 import importlib
 
 _API = ("CCMethod", "CenCC", "CSPC", "CSPatchMatch", "GrdPC", "GetCCType", "GrdCC", "IPlaneCost", "Plane", "PreCSPC",
-        "PreSSPC", "kLeft", "kRight", "set_thread_stream", "PairBatch")
+        "PreSSPC", "kLeft", "kRight", "set_thread_stream", "PatchMatchBatch")
 _LIB = ("CspmError", "LIB_PATH", "SCHEDULE_RASTER", "SCHEDULE_REDBLACK", "SCHEDULE_REDBLACK8", "STAGE_INIT", "STAGE_PLANE2DISP", "STAGE_POSTPROC",
         "STAGE_REFINE", "STAGE_SPATIAL", "STAGE_VIEW")
 __all__ = ["CspmError", "CCMethod", "GrdCC", "CenCC", "GetCCType", "IPlaneCost", "PreSSPC", "PreCSPC", "GrdPC", "CSPC", "Plane",

@@ -60,6 +60,7 @@ SIGNATURES = {
     "cspm_pm_create": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]),
     "cspm_pm_destroy": (None, [C.c_void_p]),
     "cspm_pm_patchmatch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "cspm_pm_patchmatch_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "cspm_pm_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cspm_pm_get_dis": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_int]),
     "cspm_pm_set_dis": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_int]),

@@ -292,3 +292,15 @@ class CSPatchMatch:
         ms = (C.c_float * 6)()
         check(dll.cspm_pm_stage_ms(self._h, ms))
         return list(ms)
+
+
+def PatchMatchBatch(patch_matches, plane_costs, iter_num, use_pp=False):
+    """cspm_pm_patchmatch_batch: CSPatchMatch.PatchMatch for several independent pairs of identical geometry at
+    once (throughput mode: the pairs' spatial sweeps share one launch).  Same results as calling
+    pm.PatchMatch(iter_num, pc, use_pp) pair by pair."""
+    n = len(patch_matches)
+    if n != len(plane_costs) or n == 0:
+        raise CspmError(_lib.EINVAL, "need as many plane costs as patch-match handles, at least one")
+    pms = (C.c_void_p * n)(*[pm._h for pm in patch_matches])
+    pcs = (C.c_void_p * n)(*[pc._h for pc in plane_costs])
+    check(dll.cspm_pm_patchmatch_batch(pms, pcs, n, iter_num, int(bool(use_pp))))

@@ -20,7 +20,7 @@
 #define CSPM_PROFILE_LANES 0
 #endif
 #ifndef CSPM_COOP_CS
-#define CSPM_COOP_CS 0
+#define CSPM_COOP_CS 1
 #endif
 // -DCSPM_SP_PROFILE=1: cycle accounting inside the ring sweep (clock64 + global counters on the critical path of
 // CTA 0); compiled out of the default build.
@@ -466,12 +466,15 @@ constexpr int kCoopStride = kCoopGroup * kCoopSlot;  // doubles per warp strip
 template <int CC, int LWS, int CSM, int DIR, bool ALLVALID = false>
 __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& sc, const TapCtx& t, uint32_t Ip, int x0, int x1,
                                               int y0, int y1, double a, double b, double c, double bound, double cost_prev,
-                                              double w_s, double* coop = nullptr) {
+                                              double w_s, double* coop = nullptr, bool active = true) {
+  // active = false: this lane has nothing to evaluate (its candidate was already rejected at a finer scale) and is
+  // only here to HELP the warp's survivors in the cooperative tail; it returns 0.
   const bool cross = CSM < 0 ? pc.cross_scale != 0 : CSM != 0;
   double cost = 0.0;
   // (cross-scale: the tail is a small loss there — C3 refinement 200 vs 196 ms with the grouped version, HD S=3 1 % with the
   // ungrouped one: the deeper scales run with partial warps, and the extra live state spills; CSPM_COOP_CS=1 re-enables it)
   if (kCoopLanes == 0 || CSM < 0 || (CSM != 0 && !CSPM_COOP_CS) || CC != CC_GRD || coop == nullptr) {
+    if (!active) return 0.0;
     for (int qy = y0; qy <= y1; ++qy) {
       const double q_disp_y = dadd(dmul(b, (double)qy), c);
       const int row_off = qy * sc.pitch + sc.pad;
@@ -492,7 +495,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
   // ---- bulk kernels: all lanes of the warp stay in the row loop together (same y0 / y1: one image row per warp)
   const unsigned int mask = __activemask();
   const int lane = threadIdx.x & 31;
-  bool done = false;
+  bool done = !active;
   int qy = y0;
   for (; qy <= y1; ++qy) {
 #if CSPM_PROFILE_LANES
@@ -564,7 +567,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
 template <int CC, int LWS = 0, int CSM = -1, bool COOP = true>
 __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int rx, int ry, double a, double b,
                                               double c, const double* lut_w, const double* lut_c, double bound,
-                                              double cost_prev, double w_s) {
+                                              double cost_prev, double w_s, bool active = true) {
   const ScaleDev& sc = pc.sc[s];
   const TapCtx t = make_tap_ctx(pc, s, v, lut_w, lut_c);
   const int hw = pc.half_wnd;
@@ -584,16 +587,17 @@ __device__ __forceinline__ double window_cost(const PcDev& pc, int s, int v, int
       const int fl = __double2int_rz(dadd(dmul(a, (double)qx), dadd(dmul(b, (double)qy), c)));
       ok = ok && fl > 0 && fl < t.max_disp;
     }
+    ok = ok || !active;  // a helper lane must not spoil the warp's vote
     const bool all_ok = __all_sync(__activemask(), ok);
     // per-warp strip for the cooperative tail: behind the colour table and the mbarrier of the bulk layout
     double* coop = COOP ? const_cast<double*>(lut_w) - (threadIdx.x & 15) + kBulkCoopOff + (size_t)threadIdx.y * kCoopStride : nullptr;
     if (all_ok)
-      return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
-                    : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
-    return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop)
-                  : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop);
+      return v == 0 ? window_rows<CC, LWS, CSM, -1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop, active)
+                    : window_rows<CC, LWS, CSM, 1, true>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop, active);
+    return v == 0 ? window_rows<CC, LWS, CSM, -1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop, active)
+                  : window_rows<CC, LWS, CSM, 1>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, coop, active);
   }
-  return window_rows<CC, LWS, CSM, 0>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s);
+  return window_rows<CC, LWS, CSM, 0>(pc, sc, t, Ip, x0, x1, y0, y1, a, b, c, bound, cost_prev, w_s, nullptr, active);
 }
 
 // IPlaneCost::GetPlaneCost: PreSSPC (pre_ss_pc.cc:74-118) or PreCSPC
@@ -609,6 +613,29 @@ __device__ __forceinline__ double plane_cost(const PcDev& pc, int v, int rx, int
   double cost = 0.0;
   double cur_disp = plane_disp(p, rx, ry);
   int cx = rx, cy = ry;
+  if (CSM == 1 && COOP && CSPM_COOP_CS && CC == CC_GRD) {
+    // Bulk kernels: a lane whose candidate is rejected at scale s (cost >= bound) does not leave the loop; it walks
+    // the remaining scales as a HELPER, so that the warp is complete when the few survivors reach the coarser
+    // scales and the cooperative tail (window_rows) can spread their window rows over all 32 lanes.  Without this
+    // the coarse scales ran with a handful of live lanes per warp (18 of 32 thread-instructions per instruction in
+    // the cross-scale refinement, profiles/r02_ncu_k_refine_hd_cs3.txt).  The loop ends when every lane is done.
+    const unsigned int m = __activemask();
+    bool fin = false;
+    for (int s = 0; s < pc.scale_num; ++s) {
+      PlaneD q = p;
+      update_param(q, (double)cx, (double)cy, cur_disp);
+      const double sc_cost = window_cost<CC, LWS, CSM, COOP>(pc, s, v, cx, cy, q.a, q.b, q.c, lut_w, lut_c, bound, cost, pc.scale_wgt[s], !fin);
+      if (!fin) {
+        cost = dadd(cost, dmul(sc_cost, pc.scale_wgt[s]));
+        if (cost >= bound) fin = true;
+      }
+      if (__all_sync(m, fin)) break;
+      cy /= 2;
+      cx /= 2;
+      cur_disp = ddiv(cur_disp, 2.0);
+    }
+    return cost;
+  }
   for (int s = 0; s < pc.scale_num; ++s) {
     PlaneD q = p;
     update_param(q, (double)cx, (double)cy, cur_disp);

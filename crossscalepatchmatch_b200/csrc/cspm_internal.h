@@ -154,6 +154,7 @@ struct cspm_pm {
   int* wave_list = nullptr;              // [2][w*h]
   unsigned int* wave_count = nullptr;    // [2]
   unsigned long long* wave_stats = nullptr;  // [4], accumulated over the sweeps of a call
+  void* wave_pairs = nullptr;            // device array of per-pair descriptors for batched sweeps (kMaxBatch entries)
   // post-processing scratch
   int* valid[2] = {nullptr, nullptr};
   uint8_t* dis_tmp = nullptr;

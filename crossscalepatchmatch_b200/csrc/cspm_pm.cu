@@ -531,6 +531,71 @@ static int spatial_cta_cap() {
   return e ? std::max(1, atoi(e)) : 0;
 }
 
+constexpr int kMaxBatch = 16;  // pairs per batched sweep
+
+// One wavefront sweep (cspm_pm_wave.cuh) over n >= 1 pairs of identical geometry in a single cooperative launch
+// on pm[0]'s stream, followed per pair by the compaction and the exact cost fix-up of the pixels that adopted a
+// plane.  Returns false if the launch is refused (the caller falls back to per-diagonal launches).
+static bool launch_wave(cspm_pm* const* pm, const cspm_pc* const* pc, int npairs, int rev, int sms, int cap) {
+  cspm_pm* pm0 = pm[0];
+  const PcDev& pcd0 = pc[0]->dev;
+  const int wnd = 2 * pcd0.half_wnd + 1;
+  const size_t n = (size_t)pm0->w * pm0->h;
+  cudaStream_t st = pm0->stream;
+  const bool batch = npairs > 1;
+  void (*kern)(PcDev, PmDev, const WvPair*, int, int, unsigned int*, uint8_t*, unsigned long long*, double, int) = nullptr;
+  if (batch) CSPM_DISPATCH_CC(pcd0.cc_kind, kern = k_spatial_wave<CC, true>);
+  else CSPM_DISPATCH_CC(pcd0.cc_kind, kern = k_spatial_wave<CC, false>);
+  int occ = 0;
+  CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWvSmemBytes));
+  CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWvThreads, kWvSmemBytes));
+  if (occ < 1) return false;
+  std::vector<WvPair> desc(npairs);
+  bool monotone = true;
+  for (int p = 0; p < npairs; ++p) {
+    desc[p].pc = pc[p]->dev;
+    desc[p].pm = pm_dev(pm[p]);
+    desc[p].pm.cost_consistent = pm[p]->cost_owner == pc[p]->uid;
+    desc[p].changed = pm[p]->wave_changed;
+    monotone = monotone && pc[p]->dev.monotone;
+    CSPM_CUDA(cudaMemsetAsync(pm[p]->wave_changed, 0, 2 * n, st));
+    CSPM_CUDA(cudaMemsetAsync(pm[p]->wave_count, 0, 2 * sizeof(unsigned int), st));
+  }
+  if (batch) CSPM_CUDA(cudaMemcpyAsync(pm0->wave_pairs, desc.data(), sizeof(WvPair) * npairs, cudaMemcpyHostToDevice, st));
+  // a CTA only helps while it has a pixel: never more CTAs than the longest diagonal has pixels
+  int grid = std::min(sms, std::min(pm0->w, pm0->h));
+  if (cap) grid = std::min(grid, cap);
+  CSPM_CUDA(cudaMemsetAsync(pm0->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, st));
+  // |row-major chain - tree sum| <= eps * tree sum for n non-negative addends (header of cspm_pm_wave.cuh)
+  double eps = 4.0 * (double)wnd * wnd * pcd0.scale_num * 1.1102230246251565e-16;
+  static const bool env_exact = [] { const char* e = getenv("CSPM_WAVE_EXACT"); return e && atoi(e) != 0; }();
+  int force_exact = (env_exact || !monotone) ? 1 : 0;
+  PcDev pc_arg = desc[0].pc;
+  PmDev pm_arg = desc[0].pm;
+  const WvPair* pairs_arg = batch ? (const WvPair*)pm0->wave_pairs : nullptr;
+  int np_arg = npairs, rev_arg = rev;
+  unsigned int* prog = pm0->grid_barrier;
+  uint8_t* changed = pm0->wave_changed;
+  unsigned long long* wst = pm0->wave_stats;
+  void* args[] = {&pc_arg, &pm_arg, &pairs_arg, &np_arg, &rev_arg, &prog, &changed, &wst, &eps, &force_exact};
+  const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kWvThreads), args, kWvSmemBytes, st);
+  if (ce != cudaSuccess) {  // e.g. SMs partly taken by another context
+    cudaGetLastError();
+    return false;
+  }
+  pm0->stats.kernel_launches++;
+  for (int p = 0; p < npairs; ++p) {
+    const PcDev& pcd = pc[p]->dev;
+    const PmDev d = desc[p].pm;
+    k_wave_compact<<<dim3((unsigned)((n + 255) / 256), 2), 256, 0, st>>>(pm[p]->wave_changed, (int)n, pm[p]->wave_list, pm[p]->wave_count);
+    CSPM_DISPATCH_CC_CS(pcd.cc_kind, pcd.cross_scale, constexpr int by = bulk_by<CS>(); bulk_smem(k_cost_fix<CC, CS>);
+                        k_cost_fix<CC, CS><<<dim3((unsigned)((n + 32 * by - 1) / (32 * by)), 2), dim3(32, by), kBulkSmemBytes, st>>>(
+                            pcd, d, pm[p]->wave_list, pm[p]->wave_count));
+    pm[p]->stats.kernel_launches += 2;
+  }
+  return true;
+}
+
 static void run_redblack(cspm_pm* pm, const cspm_pc* pc, int iter) {
   note_cost_writer(pm, pc, false);
   PmDev d = pm_dev(pm);
@@ -550,6 +615,14 @@ static void run_redblack(cspm_pm* pm, const cspm_pc* pc, int iter) {
     ev += 2ull * (uint64_t)std::max(0, pm->w - ox) * (uint64_t)std::max(0, pm->h - oy);
   }
   pm->stats.plane_evals += ev;
+  pm->stats.window_taps += (uint64_t)((double)pc->taps_per_image_eval * ((double)ev / ((double)pm->w * pm->h)));
+}
+
+static void spatial_account(cspm_pm* pm, const cspm_pc* pc) {
+  // evaluations: every pixel with an x-neighbour + every pixel with a y-neighbour, both views
+  const uint64_t ev = 2ull * ((uint64_t)(pm->w - 1) * pm->h + (uint64_t)pm->w * (pm->h - 1));
+  pm->stats.plane_evals += ev;
+  // tap count: whole-image totals minus the first scan column / row (mirror-symmetric)
   pm->stats.window_taps += (uint64_t)((double)pc->taps_per_image_eval * ((double)ev / ((double)pm->w * pm->h)));
 }
 
@@ -576,41 +649,7 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
   // many it is bound by instructions per tap and by the serial resolution of near-ties, where the ring wins.
   if (mode == SP_AUTO) mode = std::min(pm->w, pm->h) <= 3 * sms ? SP_WAVE : SP_RING;
   const int cap = spatial_cta_cap();
-  if (mode == SP_WAVE) {
-    void (*kern)(PcDev, PmDev, int, unsigned int*, uint8_t*, unsigned long long*, double, int) = nullptr;
-    CSPM_DISPATCH_CC(pcd.cc_kind, kern = k_spatial_wave<CC>);
-    CSPM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWvSmemBytes));
-    CSPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWvThreads, kWvSmemBytes));
-    if (occ < 1) mode = SP_DIAG;
-    else {
-      // a CTA only helps while it has a pixel: never more CTAs than the longest diagonal has pixels
-      int grid = std::min(sms, std::min(pm->w, pm->h));
-      if (cap) grid = std::min(grid, cap);
-      CSPM_CUDA(cudaMemsetAsync(pm->grid_barrier, 0, sizeof(unsigned int) * 32 * 1024, pm->stream));
-      CSPM_CUDA(cudaMemsetAsync(pm->wave_changed, 0, 2 * n, pm->stream));
-      CSPM_CUDA(cudaMemsetAsync(pm->wave_count, 0, 2 * sizeof(unsigned int), pm->stream));
-      // |row-major chain - tree sum| <= eps * tree sum for n non-negative addends (header of cspm_pm_wave.cuh)
-      double eps = 4.0 * (double)wnd * wnd * pcd.scale_num * 1.1102230246251565e-16;
-      static const bool env_exact = [] { const char* e = getenv("CSPM_WAVE_EXACT"); return e && atoi(e) != 0; }();
-      int force_exact = (env_exact || !pcd.monotone) ? 1 : 0;
-      int rev_arg = rev;
-      unsigned int* prog = pm->grid_barrier;
-      uint8_t* changed = pm->wave_changed;
-      unsigned long long* wst = pm->wave_stats;
-      void* args[] = {&pcd, &d, &rev_arg, &prog, &changed, &wst, &eps, &force_exact};
-      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kWvThreads), args, kWvSmemBytes, pm->stream);
-      if (ce != cudaSuccess) {  // e.g. SMs partly taken by another context: one launch per diagonal instead (same results)
-        cudaGetLastError();
-        mode = SP_DIAG;
-      } else {
-        k_wave_compact<<<dim3((unsigned)((n + 255) / 256), 2), 256, 0, pm->stream>>>(pm->wave_changed, (int)n, pm->wave_list, pm->wave_count);
-        CSPM_DISPATCH_CC_CS(pcd.cc_kind, pcd.cross_scale, constexpr int by = bulk_by<CS>(); bulk_smem(k_cost_fix<CC, CS>);
-                            k_cost_fix<CC, CS><<<dim3((unsigned)((n + 32 * by - 1) / (32 * by)), 2), dim3(32, by), kBulkSmemBytes, pm->stream>>>(
-                                pcd, d, pm->wave_list, pm->wave_count));
-        pm->stats.kernel_launches += 3;
-      }
-    }
-  }
+  if (mode == SP_WAVE && !launch_wave(&pm, &pc, 1, rev, sms, cap)) mode = SP_DIAG;
   if (mode == SP_RING) {
     const size_t smem_p = wnd == 35 ? kRingSmemBytes : EngineCfg<kSpRows>::kSmemBytes;
     void (*kern)(PcDev, PmDev, int, unsigned int*) = nullptr;
@@ -642,11 +681,32 @@ static void run_spatial(cspm_pm* pm, const cspm_pc* pc, int iter) {
       pm->stats.kernel_launches++;
     }
   }
-  // evaluations: every pixel with an x-neighbour + every pixel with a y-neighbour, both views
-  const uint64_t ev = 2ull * ((uint64_t)(pm->w - 1) * pm->h + (uint64_t)pm->w * (pm->h - 1));
-  pm->stats.plane_evals += ev;
-  // tap count: whole-image totals minus the first scan column / row (mirror-symmetric)
-  pm->stats.window_taps += (uint64_t)((double)pc->taps_per_image_eval * ((double)ev / ((double)pm->w * pm->h)));
+  spatial_account(pm, pc);
+}
+
+// SpatialPropagation of n pairs of identical geometry (cspm_pm_patchmatch_batch): one batched wavefront launch
+// where the wavefront kernel is the sweep of choice, otherwise pair after pair.
+static void run_spatial_batch(cspm_pm* const* pm, const cspm_pc* const* pc, int n, int iter) {
+  SpatialMode mode = spatial_mode();
+  int sms = 0, coop = 0;
+  CSPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pm[0]->device));
+  CSPM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, pm[0]->device));
+  // batching pays where the sweep is latency-bound; the crossover moves up with the batch (measured)
+  if (mode == SP_AUTO) mode = std::min(pm[0]->w, pm[0]->h) <= 4 * sms ? SP_WAVE : SP_RING;
+  if (n == 1 || mode != SP_WAVE || !coop || pm[0]->schedule != CSPM_SCHEDULE_RASTER) {
+    for (int p = 0; p < n; ++p) run_spatial(pm[p], pc[p], iter);
+    return;
+  }
+  const int rev = (iter % 2 == 0) ? 0 : 1;
+  for (int p0 = 0; p0 < n; p0 += kMaxBatch) {
+    const int np = std::min(kMaxBatch, n - p0);
+    for (int p = p0; p < p0 + np; ++p) note_cost_writer(pm[p], pc[p], false);
+    if (launch_wave(pm + p0, pc + p0, np, rev, sms, spatial_cta_cap())) {
+      for (int p = p0; p < p0 + np; ++p) spatial_account(pm[p], pc[p]);
+    } else {
+      for (int p = p0; p < p0 + np; ++p) run_spatial(pm[p], pc[p], iter);
+    }
+  }
 }
 
 static void run_view(cspm_pm* pm, const cspm_pc* pc, int iter) {
@@ -762,6 +822,7 @@ static cspm_pm_t* pm_create(const uint8_t* l, const uint8_t* r, bool on_device, 
       pm->wave_list = pm->arena.alloc<int>(2 * n);
       pm->wave_count = pm->arena.alloc<unsigned int>(2);
       pm->wave_stats = pm->arena.alloc<unsigned long long>(kWvStats);
+      pm->wave_pairs = pm->arena.alloc<WvPair>(kMaxBatch);
       CSPM_CUDA(cudaMemsetAsync(pm->wave_stats, 0, sizeof(unsigned long long) * kWvStats, pm->stream));
       CSPM_CUDA(cudaMemsetAsync(pm->tap_counter, 0, sizeof(unsigned long long), pm->stream));
       CSPM_CUDA(cudaStreamSynchronize(pm->stream));
@@ -856,6 +917,77 @@ int cspm_pm_patchmatch(cspm_pm_t* pm, int iter_num, const cspm_pc_t* pc, int use
       float ms = 0.f;
       CSPM_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
       pm->stage_ms[ev_stage[k]] += ms;
+    }
+  });
+}
+
+int cspm_pm_patchmatch_batch(cspm_pm_t* const* pm, const cspm_pc_t* const* pc, int n, int iter_num, int use_pp) {
+  if (n == 1 && pm && pc) return cspm_pm_patchmatch(pm[0], iter_num, pc[0], use_pp);
+  return guard([&] {
+    CSPM_REQUIRE(pm && pc && n >= 1, "null batch");
+    CSPM_REQUIRE(iter_num >= 0, "negative iteration count");
+    for (int p = 0; p < n; ++p) {
+      check_pair(pm[p], pc[p]);
+      CSPM_REQUIRE(pm[p]->device == pm[0]->device, "all pairs of a batch must live on one device");
+      CSPM_REQUIRE(pm[p]->w == pm[0]->w && pm[p]->h == pm[0]->h && pm[p]->schedule == pm[0]->schedule,
+                   "all pairs of a batch must have the same image size and schedule");
+      const cspm_pc *a = pc[p], *b = pc[0];
+      CSPM_REQUIRE(a->wnd_size == b->wnd_size && a->scale_num == b->scale_num && a->dev.cc_kind == b->dev.cc_kind &&
+                       a->dev.cross_scale == b->dev.cross_scale && a->scale_wgt == b->scale_wgt &&
+                       std::memcmp(a->dims, b->dims, sizeof a->dims) == 0,
+                   "all plane costs of a batch must be of the same kind and geometry (cost, window, scales, reg_lambda, max_disp)");
+      for (int q = 0; q < p; ++q) CSPM_REQUIRE(pm[q] != pm[p], "a pair appears twice in the batch");
+    }
+    use_device(pm[0]->device);
+    // everything runs on the first pair's stream (handles are idle between calls: every entry point synchronises)
+    struct Streams {
+      cspm_pm_t* const* pm;
+      int n;
+      std::vector<cudaStream_t> saved;
+      ~Streams() { for (int p = 0; p < n; ++p) pm[p]->stream = saved[p]; }
+    } streams{pm, n, {}};
+    for (int p = 0; p < n; ++p) {
+      streams.saved.push_back(pm[p]->stream);
+      pm[p]->stream = pm[0]->stream;
+    }
+    cudaStream_t st = pm[0]->stream;
+    struct Events {
+      std::vector<cudaEvent_t> v;
+      ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } evs;
+    std::vector<int> ev_stage;
+    auto mark = [&](int stage) {
+      cudaEvent_t e;
+      CSPM_CUDA(cudaEventCreate(&e));
+      evs.v.push_back(e);
+      CSPM_CUDA(cudaEventRecord(e, st));
+      ev_stage.push_back(stage);
+    };
+    mark(CSPM_STAGE_INIT);
+    for (int p = 0; p < n; ++p) run_init(pm[p], pc[p]);
+    for (int i = 0; i < iter_num; ++i) {
+      mark(CSPM_STAGE_SPATIAL);
+      run_spatial_batch(pm, pc, n, i);
+      mark(CSPM_STAGE_VIEW);
+      for (int p = 0; p < n; ++p) run_view(pm[p], pc[p], i);
+      mark(CSPM_STAGE_REFINE);
+      for (int p = 0; p < n; ++p) run_refine(pm[p], pc[p], i);
+    }
+    mark(CSPM_STAGE_PLANE2DISP);
+    for (int p = 0; p < n; ++p) run_plane2disp(pm[p]);
+    if (use_pp) {
+      mark(CSPM_STAGE_POSTPROC);
+      for (int p = 0; p < n; ++p) run_postproc(pm[p], pc[p]);
+    }
+    mark(-1);
+    CSPM_CUDA(cudaGetLastError());
+    for (int p = 0; p < n; ++p) sync_taps(pm[p]);
+    for (int p = 0; p < n; ++p)
+      for (int s = 0; s < 6; ++s) pm[p]->stage_ms[s] = 0.f;
+    for (size_t k = 0; k + 1 < evs.v.size(); ++k) {  // stage times of the whole batch, reported on the first pair
+      float ms = 0.f;
+      CSPM_CUDA(cudaEventElapsedTime(&ms, evs.v[k], evs.v[k + 1]));
+      pm[0]->stage_ms[ev_stage[k]] += ms;
     }
   });
 }

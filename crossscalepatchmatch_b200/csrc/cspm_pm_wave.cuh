@@ -64,7 +64,16 @@ struct WvTask {
   double m;                // the pixel's cost at the start of the step (:201,209 compare against it)
   unsigned long long idx;  // y * w + x
   int flags;               // bit0 view, bit1 x-candidate to evaluate, bit2 y-candidate to evaluate
-  int x, y, pad_;
+  int x, y, pair;          // pair: which stereo pair of a batched sweep (0 otherwise)
+};
+// One stereo pair of a batched sweep (cspm_pm_patchmatch_batch): the sweeps of several independent pairs of the
+// same geometry run in ONE cooperative launch, diagonal by diagonal in lockstep, so that the per-diagonal latency
+// (neighbour wait, barriers, decision, publish: more than half of a small image's sweep) is paid once per diagonal
+// instead of once per diagonal and pair.
+struct WvPair {
+  PcDev pc;
+  PmDev pm;
+  uint8_t* changed;
 };
 struct WvScale {  // one task at one pyramid level, as GetPlaneCost sees it (pre_cs_pc.cc:139-147,183-185)
   double abc[3][3];               // disparity plane (a, b, c) of x-candidate, y-candidate, own plane at this scale
@@ -174,9 +183,17 @@ __device__ __forceinline__ double wave_warp_sum(double v) {
   return v;
 }
 
-template <int CC>
-__global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev pm, int rev, unsigned int* progress, uint8_t* changed,
-                                                                unsigned long long* wstats, double eps, int force_exact) {
+// BATCH = false: one pair, described by the kernel parameters pc / pm / changed (constant bank).  BATCH = true:
+// npairs pairs described by pairs[] in global memory; pc / pm (pair 0) still provide everything the pairs share
+// (image size, window, scales, weights, tables).
+template <int CC, bool BATCH>
+__global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev pm, const WvPair* __restrict__ pairs, int npairs, int rev,
+                                                                unsigned int* progress, uint8_t* changed, unsigned long long* wstats,
+                                                                double eps, int force_exact) {
+  auto PC = [&](int p) -> const PcDev& { return BATCH ? pairs[p].pc : pc; };
+  auto PM = [&](int p) -> const PmDev& { return BATCH ? pairs[p].pm : pm; };
+  auto CHG = [&](int p) -> uint8_t* { return BATCH ? pairs[p].changed : changed; };
+  if (!BATCH) npairs = 1;
   extern __shared__ __align__(16) double s_dyn[];
   const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
   unsigned long long* s_mbar = bulk_mbar(s_dyn);
@@ -205,7 +222,8 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
     const int pq = npix / (int)gridDim.x, pr = npix % (int)gridDim.x;
     const int pix0 = (int)blockIdx.x * pq + min((int)blockIdx.x, pr);
     const int cnt = pq + ((int)blockIdx.x < pr ? 1 : 0);
-    const int ntasks_mine = 2 * cnt;
+    const int ntasks_pp = 2 * cnt;                // tasks (pixel x view) of one pair on this diagonal
+    const int ntasks_mine = npairs * ntasks_pp;   // all pairs of the batch, pair-major
     // dataflow synchronisation: wait until the CTAs that own my pixels' x / y neighbours have published diag - 1
     if (diag >= 2 && cnt > 0 && warp == 0) {
       const int pu_lo = max(0, diag - 1 - (pm.h - 1)), pu_hi = min(diag - 1, pm.w - 1);
@@ -232,7 +250,9 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
       const int nt = min(kWvTasks, ntasks_mine - base);
       // ---------------------------------------------------------------- set-up: one warp per task
       for (int ti = warp; ti < nt; ti += kWvWarps) {
-        const int tid = 2 * pix0 + base + ti;
+        const int pair = BATCH ? (base + ti) / ntasks_pp : 0;
+        const PmDev& pmp = PM(pair);
+        const int tid = 2 * pix0 + (base + ti) - pair * ntasks_pp;
         const int u = u_lo + (tid >> 1), t = diag - u;
         const int t_v = tid & 1;
         const int t_x = rev ? pm.w - 1 - u : u, t_y = rev ? pm.h - 1 - t : t;
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         bool on0 = u >= 1, on1 = t >= 1;
         // lanes 0..5: x-neighbour's plane, 8..13: y-neighbour's, 16..22: own plane and cost.  The neighbours were
         // written by (possibly) another SM on the previous diagonal: read through L2.
-        const double* st = pm.st[t_v];
+        const double* st = pmp.st[t_v];
         double val = 0.0;
         if (lane < 6) { if (on0) val = __ldcg(st + (size_t)lane * n + (idx - inc)); }
         else if (lane >= 8 && lane < 14) { if (on1) val = __ldcg(st + (size_t)(lane - 8) * n + (idx - (ptrdiff_t)inc * pm.w)); }
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         }
         // exact shortcut 1: a candidate that is bitwise the pixel's own plane re-evaluates to exactly the stored
         // cost (only while every stored cost is known to be GetPlaneCost of its plane) and cannot pass `<`
-        if (pm.cost_consistent) { on0 = on0 && !own0; on1 = on1 && !own1; }
+        if (pmp.cost_consistent) { on0 = on0 && !own0; on1 = on1 && !own1; }
         // exact shortcut 2: the y-neighbour carries the x-neighbour's plane: same cost, so after the x-candidate
         // was tested it can no longer be strictly lower than the minimum
         if (on0 && on1 && same) on1 = false;
@@ -267,10 +287,10 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         else if (lane >= 8 && lane < 14) T.cand[1][lane - 8] = val;
         else if (lane >= 16 && lane < 22) T.cand[2][lane - 16] = val;
         else if (lane == 22) T.m = val;
-        if (lane == 0) { T.idx = idx; T.flags = t_v | (on0 ? 2 : 0) | (on1 ? 4 : 0); T.x = t_x; T.y = t_y; }
+        if (lane == 0) { T.idx = idx; T.flags = t_v | (on0 ? 2 : 0) | (on1 ? 4 : 0); T.x = t_x; T.y = t_y; T.pair = pair; }
         if (lane < S && (on0 || on1)) {  // lane s prepares pyramid level s
           const int s = lane, cx = t_x >> s, cy = t_y >> s;
-          const ScaleDev& sc = pc.sc[s];
+          const ScaleDev& sc = PC(pair).sc[s];
           WvScale& D = ctl->sd[ti][s];
           wave_cand_at_scale(pc, c0, t_x, t_y, s, cx, cy, &D.abc[0][0], &D.abc[0][1], &D.abc[0][2]);
           wave_cand_at_scale(pc, c1, t_x, t_y, s, cx, cy, &D.abc[1][0], &D.abc[1][1], &D.abc[1][2]);
@@ -303,13 +323,14 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         const int flags = __shfl_sync(0xffffffffu, my_flags, task);
         const int cand = (e - excl_t == 0 && (flags & 2)) ? 0 : 1;
         const int t_v = flags & 1;
+        const PcDev& pcp = PC(BATCH ? ctl->task[task].pair : 0);
         double acc = 0.0;
         const int g_end = min(g1, (e + 1) * cpt);
         while (g < g_end) {
           const int rem = g - e * cpt, s = rem / cps, ch = rem - s * cps;
           const int nch = min(cps - ch, g_end - g);
-          const ScaleDev& sc = pc.sc[s];
-          const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
+          const ScaleDev& sc = pcp.sc[s];
+          const TapCtx tc = make_tap_ctx(pcp, s, t_v, lut_w, s_lut_c);
           const WvScale& D = ctl->sd[task][s];
           const double a = D.abc[cand][0], b = D.abc[cand][1], c = D.abc[cand][2];
           const int cx = D.cx, cy = D.cy;
@@ -371,12 +392,12 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
 #endif
           } else if (best >= 0) {
             const int v = T.flags & 1;
-            double* st = pm.st[v];
+            double* st = PM(T.pair).st[v];
             const double* p = T.cand[best];
             st[T.idx] = p[0]; st[n + T.idx] = p[1]; st[2 * n + T.idx] = p[2];
             st[3 * n + T.idx] = p[3]; st[4 * n + T.idx] = p[4]; st[5 * n + T.idx] = p[5];
             st[6 * n + T.idx] = best == 0 ? T0 : T1;  // placeholder until k_cost_fix
-            changed[(size_t)v * n + T.idx] = 1;
+            CHG(T.pair)[(size_t)v * n + T.idx] = 1;
             st_fast += 1;
           }
         }
@@ -398,12 +419,14 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         const int ti = ctl->amb[ai];
         const WvTask& T = ctl->task[ti];
         const int flags = T.flags, t_v = flags & 1;
+        const PcDev& pcp = PC(T.pair);
+        const PmDev& pmp = PM(T.pair);
         const bool on0 = (flags & 2) != 0, on1 = (flags & 4) != 0;
         bool ge0 = true, ge1o = true, ge10 = true;  // this thread's taps: t0 >= own, t1 >= own, t1 >= t0
         if (!force_exact) {
           for (int s = 0; s < S; ++s) {
-            const ScaleDev& sc = pc.sc[s];
-            const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
+            const ScaleDev& sc = pcp.sc[s];
+            const TapCtx tc = make_tap_ctx(pcp, s, t_v, lut_w, s_lut_c);
             const WvScale& D = ctl->sd[ti][s];
             for (int k = threadIdx.x; k < wtaps; k += kWvThreads) {
               const double to = wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[2][0], D.abc[2][1], D.abc[2][2], hw, wnd, wtaps, magic, k);
@@ -418,7 +441,7 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         const int votes = __syncthreads_and((ge0 ? 1 : 0)) | (__syncthreads_and((ge1o ? 1 : 0)) << 1) | (__syncthreads_and((ge10 ? 1 : 0)) << 2);
         // the decision with the certificates as extra knowledge (CTA-uniform)
         const double m = T.m, T0 = ctl->amb_T[ai][0], T1 = ctl->amb_T[ai][1];
-        const bool cert_ok = !force_exact && pm.cost_consistent;
+        const bool cert_ok = !force_exact && pmp.cost_consistent;
         int best = -1;
         bool open_q = force_exact != 0;
         if (!open_q) {
@@ -444,20 +467,20 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
         }
         if (!open_q) {
           if (best >= 0 && threadIdx.x == 0) {
-            double* st = pm.st[t_v];
+            double* st = pmp.st[t_v];
             const double* p = T.cand[best];
             st[T.idx] = p[0]; st[n + T.idx] = p[1]; st[2 * n + T.idx] = p[2];
             st[3 * n + T.idx] = p[3]; st[4 * n + T.idx] = p[4]; st[5 * n + T.idx] = p[5];
             st[6 * n + T.idx] = best == 0 ? T0 : T1;  // placeholder until k_cost_fix
-            changed[(size_t)t_v * n + T.idx] = 1;
+            CHG(T.pair)[(size_t)t_v * n + T.idx] = 1;
           }
           continue;
         }
         // Step B
         double cost = 0.0;  // lane 0 / 1 of warp 0: the candidate's running cost over the scales
         for (int s = 0; s < S; ++s) {
-          const ScaleDev& sc = pc.sc[s];
-          const TapCtx tc = make_tap_ctx(pc, s, t_v, lut_w, s_lut_c);
+          const ScaleDev& sc = pcp.sc[s];
+          const TapCtx tc = make_tap_ctx(pcp, s, t_v, lut_w, s_lut_c);
           const WvScale& D = ctl->sd[ti][s];
           for (int k = threadIdx.x; k < wtaps; k += kWvThreads) {
             ctl->xbuf[0][k] = on0 ? wave_tap<CC, 0>(tc, sc, D.cx, D.cy, D.Ip, D.abc[0][0], D.abc[0][1], D.abc[0][2], hw, wnd, wtaps, magic, k) : 0.0;
@@ -496,7 +519,7 @@ __global__ void __launch_bounds__(kWvThreads, 1) k_spatial_wave(PcDev pc, PmDev 
               PlaneD p;
               const double* c = T.cand[bb];
               p.nx = c[0]; p.ny = c[1]; p.nz = c[2]; p.a = c[3]; p.b = c[4]; p.c = c[5];
-              store_plane(pm.st[t_v], n, (size_t)T.idx, p, min_cost);
+              store_plane(pmp.st[t_v], n, (size_t)T.idx, p, min_cost);
             }
             st_exact += 1;
           }

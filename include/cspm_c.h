@@ -149,6 +149,13 @@ void cspm_pm_destroy(cspm_pm_t* pm);
  * live on the same device.  Synchronous: returns when the disparity maps are
  * final in device memory. */
 int cspm_pm_patchmatch(cspm_pm_t* pm, int iter_num, const cspm_pc_t* pc, int use_pp);
+/* The same for n independent stereo pairs of identical geometry (image size, schedule; plane costs of the same kind,
+ * window, scales, reg_lambda and max_disp) on one device: results are exactly those of n separate
+ * cspm_pm_patchmatch calls.  The pairs' SpatialPropagation sweeps share one cooperative launch and advance
+ * diagonal by diagonal in lockstep, so the per-diagonal latency that dominates small images is paid once per
+ * batch (throughput mode; the reference processes one pair per process, main.cc:57-139).  The call runs on the
+ * first pair's stream; counters of the shared sweep and the stage times of the whole batch are reported on pm[0]. */
+int cspm_pm_patchmatch_batch(cspm_pm_t* const* pm, const cspm_pc_t* const* pc, int n, int iter_num, int use_pp);
 /* One stage of the loop above (CSPM_STAGE_*); `iter` selects scan direction
  * and RNG stream exactly as the loop index i does in cs_patchmatch.cc:65-102. */
 int cspm_pm_stage(cspm_pm_t* pm, int stage, int iter, const cspm_pc_t* pc);

@@ -295,7 +295,7 @@ def test_sweep_implementations_and_grid_caps(env):
     if os.environ.get("CSPM_NESTED_TEST"):
         pytest.skip("nested run")
     here = os.path.abspath(__file__)
-    sel = "test_stages_bit_exact or test_spatial_shortcuts or test_full_patchmatch_bit_exact or test_other_window_sizes"
+    sel = "test_stages_bit_exact or test_spatial_shortcuts or test_full_patchmatch_bit_exact or test_other_window_sizes or test_batch"
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", sel],
                          env={**os.environ, **env, "CSPM_NESTED_TEST": "1"}, capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, f"{env}:\n{out.stdout[-3000:]}\n{out.stderr[-1500:]}"
@@ -329,6 +329,36 @@ def test_redblack_schedules_match_oracle(cspm, orc_lib, pair, schedule, S, lam):
     raster = cspm.CSPatchMatch(l, r, D, 4, seed=11)
     raster.PatchMatch(2, pg, True)
     assert not np.array_equal(raster.planes(0)[1], mg.planes(0)[1])
+
+
+@pytest.mark.parametrize("S,lam,npairs", [(0, 0.0, 3), (3, 0.3, 2), (0, 0.0, 5)])
+def test_batch_matches_individual_runs(cspm, orc_lib, S, lam, npairs):
+    """cspm_pm_patchmatch_batch: several independent pairs whose spatial sweeps share one cooperative launch
+    (lockstep diagonals, pair-major task list) must give exactly what pair-by-pair calls give — and the first
+    pair is also checked against the oracle."""
+    w, h, d = 80, 60, 16
+    cc = cspm.GetCCType("GRD")
+    pairs = [make_pair(w, h, d, 0xC5B20000 + 17 * k)[:2] for k in range(npairs)]
+    mk_pc = lambda l, r: cspm.PreSSPC(l, r, d, 35, cc) if S == 0 else cspm.PreCSPC(l, r, d, 35, S, cc, lam)
+    pcs = [mk_pc(l, r) for l, r in pairs]
+    solo = [cspm.CSPatchMatch(l, r, d, 4, seed=100 + k) for k, (l, r) in enumerate(pairs)]
+    for pm, pc in zip(solo, pcs):
+        pm.PatchMatch(2, pc, True)
+    batch = [cspm.CSPatchMatch(l, r, d, 4, seed=100 + k) for k, (l, r) in enumerate(pairs)]
+    cspm.PatchMatchBatch(batch, pcs, 2, True)
+    for k, (a, b) in enumerate(zip(solo, batch)):
+        _same_state(a, b, f"pair {k} of the batch")
+        for v in (0, 1):
+            assert np.array_equal(a.dis(v), b.dis(v))
+    l, r = pairs[0]
+    po = orc.PlaneCost(orc_lib, l, r, d, 35, S, lam)
+    mo = orc.PatchMatch(orc_lib, l, r, d, 4, seed=100)
+    mo.patchmatch(2, po, True)
+    _same_state(mo, batch[0], "batch pair 0 vs oracle")
+    # mixed geometry is rejected
+    other = cspm.CSPatchMatch(l[:50].copy(), r[:50].copy(), d, 4)
+    with pytest.raises(cspm.CspmError):
+        cspm.PatchMatchBatch([batch[0], other], [pcs[0], mk_pc(l[:50].copy(), r[:50].copy())], 1, False)
 
 
 def test_error_behaviour(cspm, pair):
