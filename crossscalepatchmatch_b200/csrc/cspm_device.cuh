@@ -30,6 +30,9 @@
 #ifndef CSPM_COOP_LANES
 #define CSPM_COOP_LANES 8
 #endif
+#ifndef CSPM_COOP_LANES_CS
+#define CSPM_COOP_LANES_CS 8
+#endif
 #ifndef CSPM_TAP_UNROLL
 #define CSPM_TAP_UNROLL 5
 #endif
@@ -515,7 +518,7 @@ __device__ __forceinline__ double window_rows(const PcDev& pc, const ScaleDev& s
     }
     const unsigned int alive = __ballot_sync(mask, !done);
     if (alive == 0u) return cost;
-    if (mask == 0xffffffffu && __popc(alive) <= kCoopLanes && 2 * pc.half_wnd + 1 <= 35) { ++qy; break; }
+    if (mask == 0xffffffffu && __popc(alive) <= (CSM == 1 ? CSPM_COOP_LANES_CS : kCoopLanes) && 2 * pc.half_wnd + 1 <= 35) { ++qy; break; }
   }
   // ---- cooperative tail: rows qy .. y1 of the surviving lanes, kCoopGroup survivors at a time.  The taps of the
   // group's rows are laid end to end (survivor k, tap j <-> index k * wnd + j) and dealt to the 32 lanes pass by
