@@ -8,7 +8,8 @@ Same flags, gflags syntax (--name=value, --name value, --flag / --noflag for boo
   --cc_name                   GRD | CEN                      (GetCCType, main.cc:39-55)
   --use_cs --reg_lambda       PreCSPC with scale_num = 5     (main.cc:96-104), else PreSSPC
   --use_pp                    post-processing                (cs_patchmatch.cc:347-588)
-plus two that the reference does not have: --seed (RNG contract of include/cspm_c.h; default 0x5EED) and --device.
+plus three that the reference does not have: --seed (RNG contract of include/cspm_c.h; default 0x5EED), --device and
+--schedule=raster|redblack|redblack8 (raster = the reference's order, the default; include/cspm_c.h).
 
 Image decoding / encoding is host plumbing outside the hot path; everything between
 imread and imwrite runs in libcspm_b200.so.  No CPU fallback: without a CUDA device the run fails.
@@ -21,8 +22,9 @@ import time
 DEFAULTS = {  # main.cc:23-34
     "l_img_file": "l_img.png", "r_img_file": "r_img.png", "l_dis_file": "l_dis.png", "r_dis_file": "r_dis.png",
     "max_dis": 0, "dis_scale": 0, "cc_name": "CCName", "use_cs": False, "use_pp": False, "reg_lambda": 0.0,
-    "seed": 0x5EED, "device": 0,
+    "seed": 0x5EED, "device": 0, "schedule": "raster",
 }
+SCHEDULES = {"raster": 0, "redblack": 1, "redblack8": 2}
 
 
 def parse_flags(argv):
@@ -89,7 +91,11 @@ def main(argv=None) -> int:
             plane_cost = PreCSPC(l_img, r_img, F["max_dis"], wnd_size, scale_num, cc_cost, F["reg_lambda"], device=F["device"])
         else:
             plane_cost = PreSSPC(l_img, r_img, F["max_dis"], wnd_size, cc_cost, device=F["device"])
-        patch_match = CSPatchMatch(l_img, r_img, F["max_dis"], F["dis_scale"], seed=F["seed"], device=F["device"])
+        if F["schedule"] not in SCHEDULES:
+            print(f"Error: unknown schedule '{F['schedule']}' (raster | redblack | redblack8)")
+            return 1
+        patch_match = CSPatchMatch(l_img, r_img, F["max_dis"], F["dis_scale"], seed=F["seed"], device=F["device"],
+                                   schedule=SCHEDULES[F["schedule"]])
         patch_match.PatchMatch(max_iter, plane_cost, F["use_pp"])
         l_dis, r_dis = patch_match.dis(0), patch_match.dis(1)
         print(f"{bar}\nTotal Time: {time.perf_counter() - t0:.6g}\n{bar}")  # main.cc:119-125

@@ -27,15 +27,18 @@ def _lib():
         _dll = C.CDLL(SYNTH_LIB_PATH)
         _dll.cspm_synth_make_pair.restype = C.c_int
         _dll.cspm_synth_make_pair.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        _dll.cspm_synth_make_pair_variant.restype = C.c_int
+        _dll.cspm_synth_make_pair_variant.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     return _dll
 
 
-def make_pair(w: int, h: int, max_dis: int, seed: int = SEED_BASE):
-    """Return (left_bgr, right_bgr, gt_left_disparity): uint8 HxWx3 (BGR), f64 HxW."""
+def make_pair(w: int, h: int, max_dis: int, seed: int = SEED_BASE, variant: int = 0):
+    """Return (left_bgr, right_bgr, gt_left_disparity): uint8 HxWx3 (BGR), f64 HxW.
+    variant > 0: the same scene (ground truth) as variant 0 under a different, statistically equivalent texture."""
     left = np.empty((h, w, 3), np.uint8)
     right = np.empty((h, w, 3), np.uint8)
     gt = np.empty((h, w), np.float64)
-    rc = _lib().cspm_synth_make_pair(w, h, max_dis, seed, left.ctypes.data, right.ctypes.data, gt.ctypes.data)
+    rc = _lib().cspm_synth_make_pair_variant(w, h, max_dis, seed, variant, left.ctypes.data, right.ctypes.data, gt.ctypes.data)
     if rc != 0:
         raise ValueError(f"cspm_synth_pair({w}, {h}, {max_dis}) failed")
     return left, right, gt

@@ -45,8 +45,9 @@ static inline uint64_t cspm_synth_at(uint64_t key, uint64_t idx) {
   return cspm_splitmix64(&s);
 }
 
-/* H x W x 3 texture, BGR interleaved */
-static inline void cspm_synth_texture(uint64_t* rng, int w, int h, uint8_t* out) {
+/* H x W x 3 texture, BGR interleaved.  salt != 0: same spectrum (frequencies, amplitudes) with other phases and other
+ * per-pixel noise — a different image with the same statistics. */
+static inline void cspm_synth_texture(uint64_t* rng, int w, int h, uint8_t* out, uint64_t salt) {
   double fx[3][CSPM_SYNTH_WAVES], fy[3][CSPM_SYNTH_WAVES], ph[3][CSPM_SYNTH_WAVES], amp[3][CSPM_SYNTH_WAVES];
   double cfx[3][CSPM_SYNTH_WAVES], sfx[3][CSPM_SYNTH_WAVES];
   for (int c = 0; c < 3; ++c)
@@ -54,11 +55,12 @@ static inline void cspm_synth_texture(uint64_t* rng, int w, int h, uint8_t* out)
       fx[c][k] = cspm_synth_uniform(rng, -0.35, 0.35);
       fy[c][k] = cspm_synth_uniform(rng, -0.35, 0.35);
       ph[c][k] = cspm_synth_uniform(rng, 0.0, 6.283185307179586);
+      if (salt) ph[c][k] += 6.283185307179586 * ((double)(cspm_synth_at(salt, (uint64_t)(c * CSPM_SYNTH_WAVES + k)) >> 11) * (1.0 / 9007199254740992.0));
       amp[c][k] = cspm_synth_uniform(rng, 6.0, 22.0);
       cfx[c][k] = cos(fx[c][k]);
       sfx[c][k] = sin(fx[c][k]);
     }
-  const uint64_t noise_key = cspm_splitmix64(rng);
+  const uint64_t noise_key = cspm_splitmix64(rng) ^ (salt * 0x9FB21C651E98DF25ull);
   for (int y = 0; y < h; ++y) {
     double s[3][CSPM_SYNTH_WAVES], co[3][CSPM_SYNTH_WAVES];
     for (int c = 0; c < 3; ++c)
@@ -112,8 +114,12 @@ static inline void cspm_synth_disparity(uint64_t* rng, int w, int h, int max_dis
 }
 
 /* left / right: H x W x 3 uint8 BGR (stride 3*w); gt (may be NULL): H x W f64 left-view disparity.
+ * variant: 0 = the pair of `seed`; v > 0 = the SAME scene (ground-truth disparity of `seed`) under a texture of the same
+ * spectrum with other phases and other noise — distinct images whose processing cost is the same, which is what a
+ * weak-scaling run wants on every GPU (the benchmark's pair k of a multi-GPU job is variant k of the configuration's seed).
  * Returns 0, or -1 on bad arguments / allocation failure. */
-static inline int cspm_synth_pair(int w, int h, int max_dis, uint64_t seed, uint8_t* left, uint8_t* right, double* gt) {
+static inline int cspm_synth_pair_variant(int w, int h, int max_dis, uint64_t seed, uint64_t variant, uint8_t* left, uint8_t* right,
+                                          double* gt) {
   if (w <= 0 || h <= 0 || max_dis < 1 || !left || !right) return -1;
   const size_t n = (size_t)w * h;
   double* g = gt ? gt : (double*)malloc(n * sizeof(double));
@@ -126,9 +132,10 @@ static inline int cspm_synth_pair(int w, int h, int max_dis, uint64_t seed, uint
     return -1;
   }
   uint64_t rng = seed;
-  cspm_synth_texture(&rng, w, h, left);
+  const uint64_t salt = variant * 0xD1B54A32D192ED03ull; /* 0 for variant 0 */
+  cspm_synth_texture(&rng, w, h, left, salt);
   cspm_synth_disparity(&rng, w, h, max_dis, g);
-  cspm_synth_texture(&rng, w, h, fill); /* fresh texture for disocclusions */
+  cspm_synth_texture(&rng, w, h, fill, salt ? salt + 1 : 0); /* fresh texture for disocclusions */
   for (int y = 0; y < h; ++y) {
     const double* gy = g + (size_t)y * w;
     const uint8_t* ly = left + (size_t)y * w * 3;
@@ -159,6 +166,10 @@ static inline int cspm_synth_pair(int w, int h, int max_dis, uint64_t seed, uint
   free(fill);
   free(dr);
   return 0;
+}
+
+static inline int cspm_synth_pair(int w, int h, int max_dis, uint64_t seed, uint8_t* left, uint8_t* right, double* gt) {
+  return cspm_synth_pair_variant(w, h, max_dis, seed, 0, left, right, gt);
 }
 
 #endif /* CSPM_SYNTH_H_ */

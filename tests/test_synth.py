@@ -29,6 +29,17 @@ def test_generator_is_deterministic_and_pinned():
     assert np.abs(l[y, x].astype(int) - r[y, x - d].astype(int)).max() <= 40
 
 
+def test_variants_share_the_scene():
+    from crossscalepatchmatch_b200.synth import SEED_BASE, make_pair
+
+    l0, r0, g0 = make_pair(96, 64, 20, SEED_BASE + 3)
+    l1, r1, g1 = make_pair(96, 64, 20, SEED_BASE + 3, variant=1)
+    l2, r2, g2 = make_pair(96, 64, 20, SEED_BASE + 3, variant=2)
+    assert np.array_equal(g0, g1) and np.array_equal(g0, g2), "variants keep the ground-truth disparity"
+    assert not np.array_equal(l0, l1) and not np.array_equal(l1, l2) and not np.array_equal(r0, r1)
+    assert abs(float(l0.mean()) - float(l1.mean())) < 6 and abs(float(l0.std()) - float(l1.std())) < 6
+
+
 PIN_96x64x20 = "d083e3bf1d80963e627df612da9043894bd22fa4"
 
 
