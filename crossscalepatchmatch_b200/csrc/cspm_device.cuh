@@ -14,6 +14,12 @@
 #ifndef CSPM_SP_RING
 #define CSPM_SP_RING 16
 #endif
+// producer items in flight per thread in the ring sweep (1: one item per loop iteration; 2: two, branch-free).
+// Measured at HD (spatial stage, ms): 640 threads ILP 1 / 2: 216.1 / 214.9; 512 threads ILP 2 (128 registers, no
+// spills): 208.5; 768 threads ILP 2 (80 registers, spills): 232.6.  Cross-scale and 960x540 are unchanged.
+#ifndef CSPM_RING_ILP
+#define CSPM_RING_ILP 2
+#endif
 // -DCSPM_PROFILE_LANES=1: diagnostic build that histograms, per executed window row of the bulk kernels, how many
 // lanes of the warp were still evaluating (read back with cspm_debug_lane_hist; scratch/lane_hist.py).
 #ifndef CSPM_PROFILE_LANES
@@ -1022,6 +1028,78 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
       const double k_grd = pc.k_grd;
       const unsigned int magic_row = 0xFFFFFFFFu / (unsigned int)row_items + 1u;
       const int total = WND * row_items;
+#if CSPM_RING_ILP == 2
+      // Two items per thread and iteration (rows r and ~r + 1 of the window), written as straight-line, branch-free
+      // code — coordinates clamped for addressing, results selected at the end — so that the loads of the second
+      // item are in flight while the first is computed: a producer thread is otherwise one ~190-instruction
+      // dependent chain per window row, and the consumer waits for it.
+      for (int it = threadIdx.x; it < total; it += 2 * kProducers) {
+        int rr[2], gg[2], xx[2], fl[2];
+        bool okk[2];
+        double tv[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int itk = it + k * kProducers;
+          okk[k] = itk < total;
+          const int itc = okk[k] ? itk : it;
+          rr[k] = (int)__umulhi((unsigned int)itc, magic_row);
+          const int rem = itc - rr[k] * row_items;
+          gg[k] = rem / WND;
+          xx[k] = rem - gg[k] * WND;
+        }
+        if (rr[1] >= kRing) {  // ring slots still unread?  (rr[1] >= rr[0])
+          while (*v_consumed <= rr[1] - kRing) __nanosleep(40);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const PairDesc& d = sm.pd[gg[k]];
+          fl[k] = *reinterpret_cast<const volatile int*>(&d.flags);
+          const int qy = d.cy + rr[k] - HW, qx = d.cx + xx[k] - HW;
+          const bool inb = qy >= 0 && qy < sh && qx >= 0 && qx < sw;
+          const int qyc = min(max(qy, 0), sh - 1), qxc = min(max(qx, 0), sw - 1);
+          const ViewCtx& vc = sm.ctl->view[fl[k] & 1];
+          TapCtx tc;
+          tc.col_v = vc.col_v;
+          tc.grd_v = vc.grd_v;
+          tc.hi_v = vc.hi_v;
+          tc.cg_v = vc.cg_v;
+          tc.raw.cg_o = vc.cg_o;
+          tc.raw.k_grd27 = pc.k_grd27;
+          tc.raw.cg_exp_hi = pc.cg_exp_hi;
+          tc.lut_w = sm.lut_w;
+          tc.raw.col_o = vc.col_o;
+          tc.raw.grd_o = vc.grd_o;
+          tc.raw.hi_o = vc.hi_o;
+          tc.raw.w = sw;
+          tc.raw.lut_c = sm.lut_c;
+          tc.raw.k_grd = k_grd;
+          tc.raw.dir = vc.dir;
+          tc.max_cost = vc.max_cost;
+          tc.max_disp = smaxd;
+          const int row_off = qyc * spitch + spad;
+          uint32_t Iq;
+          double gqp;
+          load_guide<CC>(tc, row_off + qxc, &Iq, &gqp);
+          const double wgt = sm.lut_w[__vsadu4(d.Ip, Iq)];
+          const double qyd = (double)qyc;
+          const double v0 = tap_value<CC>(tc, row_off, qxc, Iq, gqp, wgt, d.a0, dadd(dmul(d.b0, qyd), d.c0));
+          const double v1 = tap_value<CC>(tc, row_off, qxc, Iq, gqp, wgt, d.a1, dadd(dmul(d.b1, qyd), d.c1));
+          tv[k][0] = (inb && (fl[k] & 2)) ? v0 : 0.0;  // +0.0: additive identity of these non-negative sums
+          tv[k][1] = (inb && (fl[k] & 4)) ? v1 : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (okk[k] && (fl[k] & 6)) {
+            double* slot = sm.ring + (size_t)(rr[k] % kRing) * kRingRowDoubles + (2 * gg[k]) * kRingChain + xx[k];
+            slot[0] = tv[k][0];
+            slot[kRingChain] = tv[k][1];
+          }
+        }
+        __threadfence_block();
+        atomicAdd(&sm.ctl->done[rr[0]], 1);
+        if (okk[1]) atomicAdd(&sm.ctl->done[rr[1]], 1);
+      }
+#else
       for (int it = threadIdx.x; it < total; it += kProducers) {
         const int r = (int)__umulhi((unsigned int)it, magic_row);
         const int rem = it - r * row_items;
@@ -1070,6 +1148,7 @@ __device__ __forceinline__ double engine_eval_pairs_ring(const PcDev& pc, const 
         __threadfence_block();  // red.release.cta (ATOMS.ADD instead of the aggregated ATOMS.POPC.INC) was measured slower: 265 vs 221 ms per HD run
         atomicAdd(&sm.ctl->done[r], 1);
       }
+#endif
     } else {
       for (int r = 0; r < WND; ++r) {
         while (v_done[r] < row_items) __nanosleep(20);  // (a pure spin was measured slower: 225 vs 221 ms per HD run)

@@ -13,7 +13,7 @@
 #pragma once
 
 #ifndef CSPM_SP_THREADS
-#define CSPM_SP_THREADS 640
+#define CSPM_SP_THREADS 512
 #endif
 #ifndef CSPM_SP_LEANFENCE
 #define CSPM_SP_LEANFENCE 1
