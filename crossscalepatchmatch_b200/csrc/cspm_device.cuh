@@ -20,6 +20,10 @@
 #ifndef CSPM_RING_ILP
 #define CSPM_RING_ILP 2
 #endif
+// (Round 2 also measured "column mode" producers — a thread owns one (pair, window column) and walks the rows 1-5
+// at a time with the row-invariant set-up hoisted: 212-246 ms at HD against 208 with both candidates always
+// computed, 337-442 ms with compile-time partner direction and skipped candidates (divergence at pair boundaries,
+// spills at the 96 registers that 608-thread CTAs allow) — profiles/r02_variants_ring_col.txt; removed.)
 // -DCSPM_PROFILE_LANES=1: diagnostic build that histograms, per executed window row of the bulk kernels, how many
 // lanes of the warp were still evaluating (read back with cspm_debug_lane_hist; scratch/lane_hist.py).
 #ifndef CSPM_PROFILE_LANES
