@@ -29,11 +29,14 @@
 // per-diagonal critical path is ~cnt * 39 / warps chunk iterations instead of a 1225-long dependent add chain.
 #pragma once
 
+// CTA size and row unrolling, measured on 450x375 / 450x375 S=3 / 1242x375 S=3 (spatial stage, ms;
+// profiles/r02_variants_wave.txt): 768 threads x2: 36.9 / 70.3 / 171.1; 768 x4: 38.5 / 71.5 / 173.9 (80 registers, spills);
+// 640 x5: 36.1 / 71.8 / 175.9; 640 x3: 34.8 / 69.3 / 170.5.
 #ifndef CSPM_WAVE_THREADS
-#define CSPM_WAVE_THREADS 768
+#define CSPM_WAVE_THREADS 640
 #endif
 #ifndef CSPM_WAVE_UNROLL
-#define CSPM_WAVE_UNROLL 2
+#define CSPM_WAVE_UNROLL 3
 #endif
 
 // -DCSPM_WAVE_PROFILE=1: cycle accounting of one CTA (grid / 2), read back with cspm_debug_counters:
@@ -147,20 +150,24 @@ __device__ __forceinline__ double wave_eval_segment(const TapCtx& tc, const Scal
   const int sw = sc.w, sh = sc.h, pitch = sc.pitch, pad = sc.pad;
   const int qx = cx - hw + lane;
   const bool in_x = qx >= 0 && qx < sw;
-  const double ax = dmul(a, (double)qx);
+  const int qxc = min(max(qx, 0), sw - 1);
+  const double ax = dmul(a, (double)qxc);
   const int rows_end = min(ch + nch, wnd);
+  // branch-free rows (coordinates clamped for addressing, the addend selected at the end): the loads of the
+  // unrolled rows overlap instead of each row being its own divergent region
   CSPM_UNROLL(CSPM_WAVE_UNROLL)
   for (int q = ch; q < rows_end; ++q) {
     const int qy = cy - hw + q;
-    if (in_x && qy >= 0 && qy < sh) {
-      const int row_off = qy * pitch + pad;
-      uint32_t Iq;
-      double gqp;
-      load_guide<CC>(tc, row_off + qx, &Iq, &gqp);
-      const double wgt = tc.lut_w[__vsadu4(Ip, Iq) << kLutRepShift];
-      const double tv = tap_value_qd<CC, DIR, false, kLutCRepShift>(tc, row_off, qx, Iq, gqp, wgt, dadd(ax, dadd(dmul(b, (double)qy), c)));
-      acc = dadd(acc, cross ? dmul(tv, ws) : tv);
-    }
+    const bool inb = in_x && qy >= 0 && qy < sh;
+    const int qyc = min(max(qy, 0), sh - 1);
+    const int row_off = qyc * pitch + pad;
+    uint32_t Iq;
+    double gqp;
+    load_guide<CC>(tc, row_off + qxc, &Iq, &gqp);
+    const double wgt = tc.lut_w[__vsadu4(Ip, Iq) << kLutRepShift];
+    const double tv = tap_value_qd<CC, DIR, false, kLutCRepShift>(tc, row_off, qxc, Iq, gqp, wgt, dadd(ax, dadd(dmul(b, (double)qyc), c)));
+    const double tw = cross ? dmul(tv, ws) : tv;
+    acc = dadd(acc, inb ? tw : 0.0);
   }
   const int remc = wnd - 32, nrem = remc * wnd;
   for (int q = max(ch, wnd); q < ch + nch; ++q) {
