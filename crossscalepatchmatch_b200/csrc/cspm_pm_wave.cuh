@@ -59,7 +59,9 @@
 constexpr int kWvThreads = CSPM_WAVE_THREADS;
 constexpr int kWvWarps = kWvThreads / 32;
 constexpr int kWvTasks = 32;  // tasks per pass (a CTA owns <= 8 pixels x 2 views per diagonal at HD)
-constexpr int kWvSlots = 4;   // tasks one warp's contiguous run can touch: <= ceil(kWvTasks / kWvWarps) + 2
+// candidate evaluations one warp's contiguous run of chunks can touch: a pass has E <= 2 * kWvTasks evaluations of cpt
+// chunks each, a run is ceil(E * cpt / kWvWarps) chunks long and may start anywhere inside an evaluation
+constexpr int kWvSlots = (2 * kWvTasks + kWvWarps - 1) / kWvWarps + 1;
 constexpr int kWvMaxTaps = 63 * 63;  // wnd_size <= 63 (cspm_pc_create)
 
 struct WvTask {
