@@ -50,6 +50,12 @@ __device__ __forceinline__ void store_plane(double* st, size_t n, size_t i, cons
 constexpr int kBulkBySs = CSPM_BULK_BY;     // bulk kernels: 32 x kBulkBy pixels per CTA (98 KB replicated table per CTA) ...
 constexpr int kBulkByCs = CSPM_BULK_BY_CS;  // ... chosen separately for the cross-scale instantiations (more live state)
 template <bool CS> constexpr int bulk_by() { return CS ? kBulkByCs : kBulkBySs; }
+// PlaneRefinement, cross-scale: 16 warps (128 registers, no spills) measured best once the rejected lanes stay on as
+// helpers (HD S=3 refinement 805 ms against 819 at 20 warps, 838 at 24; init / view propagation prefer 20)
+#ifndef CSPM_REFINE_BY_CS
+#define CSPM_REFINE_BY_CS 16
+#endif
+template <bool CS> constexpr int refine_by() { return CS ? CSPM_REFINE_BY_CS : kBulkBySs; }
 constexpr int kBulkMinB = CSPM_BULK_MINB;  // CTAs per SM the register allocation must allow
 template <int CC, bool CS>
 __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_init(PcDev pc, PmDev pm) {
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_init(PcDev pc
 
 // ----------------------------------------------------------------- refine
 template <int CC, bool CS>
-__global__ void __launch_bounds__(32 * bulk_by<CS>(), kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
+__global__ void __launch_bounds__(32 * refine_by<CS>(), kBulkMinB) k_refine(PcDev pc, PmDev pm, int iter) {
   extern __shared__ __align__(16) double s_dyn[];
   const double* s_lut_c = bulk_lut_c(s_dyn);  // this lane's copy of the colour table
   unsigned long long* s_mbar = bulk_mbar(s_dyn);
@@ -507,7 +513,7 @@ static void run_init(cspm_pm* pm, const cspm_pc* pc) {
 
 static void run_refine(cspm_pm* pm, const cspm_pc* pc, int iter) {
   note_cost_writer(pm, pc, false);
-  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = bulk_by<CS>(); dim3 b(32, by), g((pm->w + 31) / 32, (pm->h + by - 1) / by, 2);
+  CSPM_DISPATCH_CC_CS(pc->dev.cc_kind, pc->dev.cross_scale, constexpr int by = refine_by<CS>(); dim3 b(32, by), g((pm->w + 31) / 32, (pm->h + by - 1) / by, 2);
                       bulk_smem(k_refine<CC, CS>); k_refine<CC, CS><<<g, b, kBulkSmemBytes, pm->stream>>>(pc->dev, pm_dev(pm), iter));
   pm->stats.kernel_launches++;
   pm->stats.plane_evals += 2ull * pm->n_ref * pm->w * pm->h;
