@@ -13,20 +13,31 @@
 //     |S - T| <= eps * T with eps = 4 n u (u = 2^-53; > 2 gamma_n / (1 - gamma_n), and it absorbs the 2 extra roundings
 //     per scale of the cross-scale combination);
 //   * a comparison whose two intervals do not overlap has the same outcome for S as for T: taken at once;
-//   * if they overlap (in practice: exact ties, e.g. two different planes whose windows are invalid everywhere)
-//     the task takes the EXACT path: one warp computes each window row's addends, two lanes add them in the
-//     reference's order, and the reference's comparison is applied to those sums.
+//   * if they overlap — in practice real ties: near the image border whole families of planes have all their partners
+//     outside the image and cost the same, tap by tap up to the rounding of the interpolation (~1 % of the tasks at
+//     1920x1080 D=256) — the task is UNDECIDED and goes, CTA-wide, through
+//       step A, a term-wise certificate: RN addition is monotone, so if every addend of the candidate is >= the
+//         corresponding addend of the pixel's own plane, every partial sum of its chain is too and `S_cand < m` is
+//         false without adding anything (m is GetPlaneCost of the own plane while cost_consistent); likewise
+//         y-candidate >= x-candidate term-wise gives S_1 >= S_0;
+//       step B, the exact path, for what is still open: all threads write the window's addends to shared memory,
+//         lane 0 / 1 of warp 0 add the x- / y-candidate's in the reference's row-major order, and the reference's
+//         comparison is applied to those sums.
 // A pixel that adopts a plane on the fast path gets the tree sum as a PLACEHOLDER cost and a mark in `changed`;
-// right after the sweep k_cost_fix recomputes the cost of every marked pixel with the bit-exact bulk evaluator
-// (thread per pixel, row-major order), before anything reads it.  Planes, costs and disparities therefore stay
-// bit-identical to the reference (tests: stage parity, and the same with CSPM_WAVE_EXACT=1, which sends every
-// task down the exact path).
+// right after the sweep k_wave_compact + k_cost_fix recompute the cost of every marked pixel with the bit-exact
+// bulk evaluator (thread per pixel, row-major order), before anything reads it.  Planes, costs and disparities
+// therefore stay bit-identical to the reference (tests: stage parity after every sweep; the same with
+// CSPM_WAVE_EXACT=1, which sends every task down the exact path, and with CSPM_SP_CTAS=n, which shrinks the grid;
+// the inequality and the decision logic on the CPU in tests/test_wave_bound_math.py).
 //
-// Work layout per CTA and diagonal: the CTA's tasks (pixel x view, two candidates sharing the adaptive weight) are
-// cut into chunks of 32 consecutive window taps (x scales); the chunk list is dealt to the warps in contiguous
-// runs, lanes along taps (coalesced guide / partner rows whatever the plane), each lane keeps running partial sums
-// and a warp reduces them once per task it touched.  No thread ever waits on another inside the evaluation; the
-// per-diagonal critical path is ~cnt * 39 / warps chunk iterations instead of a 1225-long dependent add chain.
+// Work layout per CTA and diagonal: a set-up phase (one warp per task = pixel x view) loads the neighbours' planes,
+// applies the two exact shortcuts and files, per pyramid level, the planes as GetPlaneCost sees them; the
+// candidates that survived are numbered, their windows are cut into chunks of 32 taps (chunk q < wnd = window row
+// q with lane <-> column, the remaining columns follow as linear chunks), and the chunk list is dealt to the warps in
+// equal contiguous runs, so every warp has the same load whatever the shortcuts removed.  Lanes keep partial sums, a
+// warp reduces once per candidate it touched, warp 0 forms the tree sums and decides.  No thread waits on another
+// inside the evaluation; the per-diagonal critical path is ~candidates * 39 / warps chunk iterations instead of a
+// 1225-long dependent add chain.  BATCH = true runs the sweeps of several independent pairs in one launch.
 #pragma once
 
 // CTA size and row unrolling, measured on 450x375 / 450x375 S=3 / 1242x375 S=3 (spatial stage, ms;
