@@ -64,6 +64,16 @@ def test_argument_validation_without_gpu():
         c.PreSSPC(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.uint8), 4, 35, c.GetCCType("GRD"))
 
 
+def test_batch_entry_point_validates_without_gpu():
+    import crossscalepatchmatch_b200 as c
+    from crossscalepatchmatch_b200 import _lib
+
+    assert _lib.dll.cspm_pm_patchmatch_batch(None, None, 0, 1, 0) == _lib.EINVAL
+    assert _lib.dll.cspm_last_error_code() == _lib.EINVAL and "batch" in _lib.last_error()
+    with pytest.raises(c.CspmError):
+        c.PatchMatchBatch([], [], 1)
+
+
 def test_headers_compile_as_c_and_cpp(tmp_path):
     """include/cspm_c.h must be plain C (the boundary is a C ABI); include/cspm.hpp is self-contained C++17."""
     import shutil
