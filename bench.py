@@ -180,6 +180,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def binding_limit(onchip):
+    """The on-chip resource of the ncu summary that is closest to its peak: what actually bounds the dominant kernel
+    (the 19 B/tap HBM model exceeds 1 by construction once windows are served from L1/L2)."""
+    if not isinstance(onchip, dict):
+        return None
+    names = {"issue_active_pct": "instruction issue slots", "l1_data_pipe_pct": "L1 data pipe (LSU wavefronts)",
+             "fp64_pipe_pct": "fp64 pipe", "xu_pipe_pct": "XU pipe (int<->f64 conversions)", "alu_pipe_pct": "ALU pipe"}
+    cands = {k: float(onchip[k]) for k in names if isinstance(onchip.get(k), (int, float))}
+    if not cands:
+        return None
+    top = max(cands, key=cands.get)
+    return {"resource": names[top], "frac_of_peak": cands[top] / 100.0,
+            "all": {names[k]: round(v / 100.0, 4) for k, v in sorted(cands.items(), key=lambda kv: -kv[1])},
+            "source": onchip.get("source")}
+
+
 def count_executed_taps(args, device):
     """Window taps the PlaneRefinement launches actually execute: a second process loads the instrumented build
     (libcspm_b200_count.so, -DCSPM_COUNT_TAPS=1: same kernels + a counter) and replays the step stage by stage."""
@@ -406,6 +422,7 @@ def run_b200(args):
                     "onchip": onchip}
         if traffic:
             roofline["dram_frac"] = traffic / (ms * 1e-3) / 1e9 / peak  # measured DRAM bytes / launch time / peak
+        roofline["binding"] = binding_limit(onchip)  # the limiter that is really closest to its peak (< 1)
         # taps the launch really executed (exact early termination skips the rest): counted by the instrumented
         # build of the same kernels on the same inputs, outside the timed region
         if not args.no_tap_count:

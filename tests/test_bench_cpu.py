@@ -28,3 +28,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64x40x12",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_binding_limit_from_the_committed_ncu_summary():
+    """roofline.binding of the bench line: the on-chip resource closest to its peak, from profiles/r02_onchip.json."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    onchip = json.load(open(os.path.join(ROOT, "profiles", "r02_onchip.json")))
+    for key in ("k_refine_ss", "k_refine_cs"):
+        b = bench.binding_limit(onchip[key])
+        assert b and 0.3 < b["frac_of_peak"] < 1.0 and b["resource"] in b["all"] and "r02_ncu_k_refine" in b["source"]
+        assert b["frac_of_peak"] == max(b["all"].values()) or abs(b["frac_of_peak"] - max(b["all"].values())) < 1e-4
+    assert bench.binding_limit(None) is None and bench.binding_limit({}) is None
